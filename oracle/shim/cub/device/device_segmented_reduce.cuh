@@ -1,0 +1,1 @@
+#include "device_scan.cuh"

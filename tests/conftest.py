@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """tests/golden/seg_ops_golden.npz → {'op/case/source': ndarray} (see oracle/gen_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "seg_ops_golden.npz"))
+    return {k.replace("__", "/"): z[k] for k in z.files}
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny): the normalised error every fp32 parity bar is written in."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
