@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py — aggregated edges/sec (fwd+bwd) of the STAR-GCN aggregation hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (rank 0)
+
+One "step" = one HeterGCN layer's aggregation on an ML-10M-shaped synthetic bipartite graph
+(BASELINE.json configs[3], dim 64, 10 rating levels, U=250; fits one GPU): for BOTH directions
+(user<-item and item<-user) the fused multi-relation gather-aggregate + relation transform +
+LeakyReLU forward and the full backward (dX through the transposed gather, dW, db).
+edges/sec = (edges of both directions) / step time  (SURVEY.md §8d).
+
+Prints ONE JSON line (rank 0).  Keys are described in DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aggregated edges/sec (fwd+bwd), dim=64, ML-10M shape"
+UNIT = "edges/s"
+AGG_UNITS = 250          # GCN.AGG.UNITS (cfg/transductive_ml_10m.yml)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml-10m")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def load_workload(name, seed=1000):
+    """Synthetic graph of the named shape; cached under /tmp because generation takes ~25 s."""
+    from stargcn_b200 import synth
+    cache = f"/tmp/stargcn_b200_{name}_{seed}.npz"
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            d = dict(R=int(z["R"]), D=int(z["D"]), n_user=int(z["n_user"]), n_item=int(z["n_item"]), nnz=int(z["nnz"]),
+                     x_user=z["x_user"], x_item=z["x_item"])
+            for side in ("user", "item"):
+                d[side] = tuple([z[f"{side}_{k}_{r}"] for r in range(d["R"])] for k in ("ep", "ptr", "sup"))
+            return d
+        except Exception:
+            pass
+    d = synth.make_layer_inputs(name, seed)
+    try:
+        flat = dict(R=d["R"], D=d["D"], n_user=d["n_user"], n_item=d["n_item"], nnz=d["nnz"], x_user=d["x_user"],
+                    x_item=d["x_item"])
+        for side in ("user", "item"):
+            for k, lst in zip(("ep", "ptr", "sup"), d[side][:3]):
+                for r, a in enumerate(lst):
+                    flat[f"{side}_{k}_{r}"] = a
+        np.savez(cache + ".tmp.npz", **flat)
+        os.replace(cache + ".tmp.npz", cache)
+    except Exception:
+        pass
+    d["user"], d["item"] = tuple(d["user"][:3]), tuple(d["item"][:3])
+    return d
+
+
+def make_params(R, D, U, seed=7):
+    rs = np.random.RandomState(seed)
+    bound = np.sqrt(3.0 / D)   # Xavier(factor_type='in') uniform, STAR-GCN.py:548
+    return ([rs.uniform(-bound, bound, (U, D)).astype(np.float32) for _ in range(R)],
+            [np.zeros(U, np.float32) for _ in range(R)])
+
+
+def algorithmic_bytes(nnz, n_seg_total, n_rows_out, D, forward):
+    """per edge 4 B index + 4 B support + 4*D B gathered row; per segment 4 B of
+    indptr and the 4*D B output row."""
+    per_edge = 8 + 4 * D
+    if forward:
+        return nnz * per_edge + n_seg_total * (4 + 4 * D)
+    return nnz * per_edge + n_rows_out * (4 + 4 * D)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.path, self.idx = None, f"/tmp/stargcn_clocks_{os.getpid()}.csv", gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU path (restated call pattern of aggregators.py:133-160 on the CPU operators)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(x_nb, ws, bs, ep_l, ptr_l, sup_l, gout, pool_fwd, pool_bwd):
+    """FullyConnected (torch CPU as the MXNet BLAS stand-in) + seg_weighted_pool at F=250 per
+    rating level, add_n, LeakyReLU(0.1); backward: data-gradient scatter (serial over nnz as in
+    seg_op.cc:232-239), dW, db, dX."""
+    import torch
+    import torch.nn.functional as F
+    xt = torch.from_numpy(x_nb)
+    pre = None
+    for w, b, e, p, s in zip(ws, bs, ep_l, ptr_l, sup_l):
+        h = F.linear(xt, torch.from_numpy(w), torch.from_numpy(b)).numpy()
+        o = pool_fwd(h[None], s[None], e, p)[0]
+        pre = o if pre is None else pre + o
+    out = np.where(pre > 0, pre, np.float32(0.1) * pre)
+    gz = np.where(pre > 0, gout, np.float32(0.1) * gout).astype(np.float32)
+    gx = torch.zeros_like(xt)
+    for w, e, p, s in zip(ws, ep_l, ptr_l, sup_l):
+        gh = torch.from_numpy(pool_bwd(gz[None], s[None], e, p, x_nb.shape[0])[0])
+        _gw = gh.t() @ xt
+        _gb = gh.sum(0)
+        gx += gh @ torch.from_numpy(w)
+    return out, gx.numpy()
+
+
+def cpu_pool_functions():
+    """oracle/_ref (the reference's own loops) when present, else the C oracle port."""
+    from oracle import ref, segops
+    if ref.available():
+        return "reference", ref.weighted_pool_fwd, ref.weighted_pool_bwd_data
+    return "port", segops.seg_weighted_pool, segops.seg_weighted_pool_bwd_data
+
+
+def run_cpu_arm(wl, steps, warmup, budget_s):
+    """Times the reference's CPU path on a bounded sample of the workload: ONE rating level of both
+    directions over the full node sets (so the FullyConnected : pooling cost ratio of a level is
+    preserved).  The level is the one whose edge share is closest to the mean share 1/R, unless a
+    calibration pass shows it cannot fit the time budget.  Returns (edges/s, info)."""
+    kind, pool_fwd, pool_bwd = cpu_pool_functions()
+    R, D = wl["R"], wl["D"]
+    ws, bs = make_params(R, D, AGG_UNITS)
+    cores = os.cpu_count() or 1
+    rs = np.random.RandomState(5)
+    shares = np.array([float(wl["user"][1][r][-1]) for r in range(R)]) / max(wl["nnz"], 1)
+    order = list(np.argsort(np.abs(shares - 1.0 / R)))            # closest to the mean share first
+    by_size = list(np.argsort(shares))
+
+    def build(r):
+        sides = []
+        for side, x_nb, n_dst in (("user", wl["x_item"], wl["n_user"]), ("item", wl["x_user"], wl["n_item"])):
+            ep_l, ptr_l, sup_l = wl[side]
+            nnz = int(ptr_l[r][-1])
+            lists = ([np.ascontiguousarray(ep_l[r][:nnz])], [ptr_l[r]], [np.ascontiguousarray(sup_l[r][:nnz])])
+            gout = rs.standard_normal((n_dst, AGG_UNITS)).astype(np.float32)
+            sides.append((x_nb, lists, gout, nnz))
+        return sides
+
+    def one_step(sides, r):
+        for x_nb, lists, gout, _ in sides:
+            cpu_reference_step(x_nb, ws[r:r + 1], bs[r:r + 1], *lists, gout, pool_fwd, pool_bwd)
+
+    # calibrate on the smallest level, then take the preferred level if it fits the budget
+    r0 = int(by_size[0])
+    sides = build(r0)
+    t0 = time.perf_counter(); one_step(sides, r0); t_small = time.perf_counter() - t0
+    e_small = sum(s[3] for s in sides)
+    r = r0
+    for cand in order:
+        cand = int(cand)
+        est = t_small * max(1.0, shares[cand] * 2 * wl["nnz"] / max(e_small, 1))
+        if est * (steps + warmup) <= budget_s:
+            r = cand
+            break
+    if r != r0:
+        sides = build(r)
+    edges = sum(s[3] for s in sides)
+    for _ in range(warmup):
+        one_step(sides, r)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step(sides, r)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    info = dict(kind=kind, cores=cores, edges_per_step=int(edges), ms_per_step=dt * 1e3,
+                sample=f"rating level {r} of {R} ({shares[r] * 100:.1f}% of the edges; {edges} of {2 * wl['nnz']}) of both "
+                       f"directions over the full node sets, reference operator order at F={AGG_UNITS}: FullyConnected, "
+                       f"seg_weighted_pool forward (OpenMP over segments, {cores} threads), LeakyReLU, data-gradient "
+                       f"scatter serial as in seg_op.cc:232-239, dW/db/dX GEMMs")
+    return edges / dt, info
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import stargcn_b200  # noqa: F401
+    from stargcn_b200 import _lib, graph
+    from stargcn_b200.graph import MultiLinkCSR
+    from stargcn_b200.layers import MultiLinkGCNAggregator
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = load_workload(args.workload)
+    R, D, U = wl["R"], wl["D"], AGG_UNITS
+    ws, bs = make_params(R, D, U)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident state: inputs live in HBM before the timed region starts ----
+    sides = {}
+    for side, x_nb, n_dst in (("user", wl["x_item"], wl["n_user"]), ("item", wl["x_user"], wl["n_item"])):
+        csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
+        agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", dropout_rate=0.0, ordinal_sharing=False,
+                                     accum="sum", in_units=D).to(dev)
+        with torch.no_grad():
+            for i in range(R):
+                getattr(agg, f"weight{i}").copy_(torch.from_numpy(ws[i]))
+                getattr(agg, f"bias{i}").copy_(torch.from_numpy(bs[i]))
+        x = torch.from_numpy(x_nb).to(dev).requires_grad_(True)
+        gout = torch.randn((n_dst, U), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+        sides[side] = dict(csr=csr, agg=agg, x=x, gout=gout, n_dst=n_dst)
+    edges_per_step = sum(s["csr"].nnz for s in sides.values())
+
+    def step():
+        for s in sides.values():
+            s["x"].grad = None
+            for p in s["agg"].parameters():
+                p.grad = None
+            out = s["agg"](s["x"], s["csr"])
+            out.backward(s["gout"])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    graph.PROFILE = []
+    _lib.reset_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    prof, graph.PROFILE = graph.PROFILE, None
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = edges_per_step * world / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (gather_rows_kernel), from events on its own stream ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    detail, tot_bytes, tot_ms = {}, 0.0, 0.0
+    for tag, a, b, csr in prof:
+        fwd = tag == "agg_fwd"
+        key = f"{tag}:{'user' if csr is sides['user']['csr'] else 'item'}"
+        by = algorithmic_bytes(csr.nnz, csr.n_seg, csr.n_nb, D, fwd)
+        d = detail.setdefault(key, dict(ms=0.0, n=0, bytes=by, edges=csr.nnz))
+        d["ms"] += a.elapsed_time(b); d["n"] += 1
+    for key, d in detail.items():
+        d["ms"] /= max(d["n"], 1)
+        d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        d["frac"] = d["gbs"] / peak_gbs
+        d["gedges_s"] = d["edges"] / (d["ms"] * 1e-3) / 1e9
+        tot_bytes += d["bytes"]; tot_ms += d["ms"]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gather_rows_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel="gather_rows_kernel (4 launches/step)", achieved=tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms else None,
+                    peak=peak_gbs, peak_source=peak_src, unit="GB/s", frac=(tot_bytes / (tot_ms * 1e-3) / 1e9 / peak_gbs) if tot_ms else None,
+                    traffic=traffic, share_of_step=tot_ms / ms_per_step if ms_per_step else None,
+                    per_launch={k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in detail.items()})
+
+    # ---- end to end through the public layer API with HOST buffers (H2D + D2H inside) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, sides, dev, world, barrier)
+
+    result = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                  ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                  data="synthetic",
+                  config=dict(workload=f"{args.workload}-shaped bipartite rating graph: {wl['n_user']} users x {wl['n_item']} items, "
+                                       f"{wl['nnz']} edges/direction, R={R} levels, D={D}, agg units={U}; one HeterGCN layer, both "
+                                       f"directions, fwd+bwd; full neighbourhood",
+                              edges_per_step_per_gpu=edges_per_step,
+                              parallelism="single GPU" if world == 1 else f"{world} independent replicas (no exchange)",
+                              l2="inputs exceed L2: ~%.0f MB of CSR/feature/intermediate traffic per step vs 126 MB L2; no flush" % (
+                                  (sum(algorithmic_bytes(s['csr'].nnz, s['csr'].n_seg, s['csr'].n_nb, 0, True) for s in sides.values()) * 2
+                                   + sum(s['n_dst'] * (R * D + U) * 4 * 3 for s in sides.values())) / 1e6)),
+                  clocks=clocks, gpu_launches=int(launches), roofline=roofline)
+    if e2e is not None:
+        result["e2e"] = e2e
+    return result, wl
+
+
+def run_e2e(args, wl, sides, dev, world, barrier):
+    """Same step through the public API starting from PINNED HOST buffers: per step the CSR lists,
+    features and upstream gradient are copied host->device, the device plan (concatenated CSR, stable
+    transpose, schedules) is rebuilt — the reference re-uploads and re-sorts per call too
+    (layers.py:366-377, seg_op.cu:882-926) — forward + backward run, and a scalar read-back ends it."""
+    import torch
+    from stargcn_b200.graph import MultiLinkCSR
+    R, D = wl["R"], wl["D"]
+    host = {}
+    h2d = 0
+    for side, x_nb in (("user", wl["x_item"]), ("item", wl["x_user"])):
+        csr = sides[side]["csr"]
+        host[side] = dict(ep=csr.end_points.cpu().pin_memory(), sup=csr.support.cpu().pin_memory(),
+                          ptr=csr.cat_indptr.cpu().pin_memory(), x=torch.from_numpy(x_nb).pin_memory())
+        h2d += sum(t.numel() * t.element_size() for t in host[side].values())
+
+    def step():
+        total = torch.zeros((), device=dev)
+        for side in ("user", "item"):
+            h, s = host[side], sides[side]
+            ep, sup, ptr = (h[k].to(dev, non_blocking=True) for k in ("ep", "sup", "ptr"))
+            x = h["x"].to(dev, non_blocking=True).requires_grad_(True)
+            csr = MultiLinkCSR.from_device(ep, sup, ptr, R, s["n_dst"], x.shape[0])
+            for p in s["agg"].parameters():
+                p.grad = None
+            out = s["agg"](x, csr)
+            loss = 0.5 * (out * out).mean()
+            loss.backward()
+            total = total + loss.detach()
+        return float(total.item())   # D2H read of the step's result
+
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    edges = sum(s["csr"].nnz for s in sides.values())
+    return dict(value=edges * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
+                d2h_bytes_per_step=4, includes="H2D of CSR+features from pinned memory, device plan rebuild "
+                "(transpose + schedules), fwd+bwd, scalar loss read-back")
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = load_workload(args.workload)
+        value, info = run_cpu_arm(wl, max(args.steps, 1), max(args.warmup, 0), budget_s=90.0)
+        line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=info["ms_per_step"], higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"{args.workload}-shaped bipartite rating graph, reference CPU operator order "
+                                         f"(FullyConnected + seg_weighted_pool per level at F={AGG_UNITS}), bounded row sample",
+                                edges_per_step=info["edges_per_step"]),
+                    cpu_baseline=dict(value=value, unit=UNIT, cores=info["cores"], kind=info["kind"], sample=info["sample"]),
+                    e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    result, wl = run_gpu_arm(args, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, info = run_cpu_arm(wl, steps=2, warmup=1, budget_s=args.cpu_baseline_seconds)
+            result["cpu_baseline"] = dict(value=v, unit=UNIT, cores=info["cores"], kind=info["kind"], sample=info["sample"])
+        print(json.dumps(result))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,172 @@
+/*
+ * stargcn_b200 — C ABI of the Blackwell-native STAR-GCN aggregation hot path.
+ *
+ * Drop-in boundary for the reference's MXNet operator plug-in
+ * (/root/reference/seg_ops_cuda/mxnet_op/seg_op.{h,cc,cu}).  The reference registers
+ * FCompute<gpu> functions that unpack TBlobs into (pointer, shape) pairs and call
+ * `seg_op::*Impl(dst, ..., req, ctx, stream)` (seg_op.h:31-177); each entry point below is
+ * what such an FCompute body would call instead.  Plain pointers and sizes only — no MXNet,
+ * torch or C++ types cross this boundary.
+ *
+ * Rules common to every entry point
+ *   - all pointers are DEVICE pointers unless the name says `_host`; float tensors are dense
+ *     row-major fp32, index tensors int32 (the only dtypes the reference accepts:
+ *     seg_op.h:232-233,410-413,530-532)
+ *   - the caller owns every buffer including scratch (`ws`), exactly as MXNet owns its
+ *     kTempSpace (seg_op.cc:365-368); the library never allocates device memory, never
+ *     synchronises `stream`, and keeps no state between calls except the thread-local
+ *     error string
+ *   - `req` is MXNet's OpReqType (SG_REQ_*): NULL returns immediately, WRITE overwrites the
+ *     whole destination (empty segments become 0), ADD accumulates into it
+ *     (seg_op.cc:188-196; exercised by test_seg_ops.py:130,152-154)
+ *   - return value: SG_OK or an SG_ERR_* code; sg_last_error() describes the last failure
+ *     on the calling thread.  Nothing ever calls exit() (the reference does: seg_op.cu:14-18)
+ */
+#ifndef STARGCN_B200_H_
+#define STARGCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *sg_stream_t; /* a cudaStream_t */
+
+enum { SG_OK = 0, SG_ERR_INVALID = 1, SG_ERR_CUDA = 2, SG_ERR_WORKSPACE = 3 };
+enum { SG_REQ_NULL = 0, SG_REQ_WRITE = 1, SG_REQ_ADD = 3 };      /* mxnet::OpReqType */
+enum { SG_POOL_SUM = 0, SG_POOL_MEAN = 1, SG_POOL_MAX = 2 };     /* SegReduceType, seg_op.h:20 */
+enum { SG_REDUCE_SUM = 0, SG_REDUCE_MAX = 2, SG_REDUCE_MIN = 3 };
+enum { SG_BCAST_ADD = 0, SG_BCAST_MUL = 1, SG_BCAST_TO = 2, SG_BCAST_SUB = 3, SG_BCAST_DIV = 4 };
+enum { SG_ACT_IDENTITY = 0, SG_ACT_LEAKY = 1, SG_ACT_RELU = 2 }; /* common.py:32-57 */
+
+const char *sg_last_error(void);
+int sg_abi_version(void);
+/* Number of kernels this library has launched (process-wide) since the last reset. */
+long long sg_launch_count(void);
+void sg_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A7  Segment bookkeeping (bit-exact integer work)
+ * replaces GetSegId::compute (seg_op.cu:91-110), the CPU seg_ids loop (seg_op.cc:226-231)
+ * and gen_row_indices_by_indptr (GraphSampler/graph_sampler.cpp:378-391)
+ * ---------------------------------------------------------------------------------------- */
+int sg_seg_ids(int32_t *seg_ids /*nnz*/, const int32_t *indptr /*n_seg+1*/, int n_seg, int nnz,
+               sg_stream_t stream);
+
+/* Stable transpose of a CSR pattern: for every destination row n (a value of `indices`) the
+ * nnz positions p that point at it, in ascending p.  Built ONCE per sampled plan and reused by
+ * every backward call, where the reference re-runs iota + radix sort + scan on every call
+ * (compute_grad_embed2, seg_op.cu:882-926; SegPool compute_grad_data, seg_op.cu:1250-1283).
+ *   t_indptr (n_nb+1), t_perm (nnz): original position p, t_seg (nnz): segment owning p */
+size_t sg_csr_transpose_ws_bytes(int n_seg, int n_nb, int nnz);
+int sg_csr_transpose(int32_t *t_indptr, int32_t *t_perm, int32_t *t_seg, const int32_t *indices,
+                     const int32_t *indptr, int n_seg, int n_nb, int nnz, void *ws, size_t ws_bytes,
+                     sg_stream_t stream);
+
+/* Segment schedule: cuts every segment of a CSR into work items of at most `chunk` edges so
+ * that heavy-tailed degree distributions load-balance across the 148 SMs.  Opaque device
+ * buffer of sg_plan_bytes(); depends on indptr only.  sg_plan_partial_rows() is the number
+ * of scratch rows (each F floats) the gather kernels need for split segments.  Entry points
+ * that accept a plan also take the `plan_chunk` it was built with (0 when plan is NULL). */
+size_t sg_plan_bytes(int n_seg, int nnz, int chunk);
+size_t sg_plan_partial_rows(int n_seg, int nnz, int chunk);
+int sg_plan_build(void *plan, size_t plan_bytes, const int32_t *indptr, int n_seg, int nnz,
+                  int chunk, sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2  seg_weighted_pool forward
+ * replaces SegWeightedPoolForward<gpu> -> SegTakeKCorrBackwardEmbed1Impl<gpu>
+ * (seg_op.h:460-476, seg_op.cu:956-979, kernel seg_op.cu:682-722)
+ *   dst[k,s,:] (=|+=) sum_{p in seg s} weights[k,p] * data[k, indices[p], :]
+ * `plan` may be NULL (one work item per segment); `partial` needs
+ * K * sg_plan_partial_rows() * F floats when a plan is given.
+ * ---------------------------------------------------------------------------------------- */
+int sg_weighted_pool_fwd(float *dst /*K,n_seg,F*/, const float *data /*K,n_nb,F*/,
+                         const float *weights /*K,nnz*/, const int32_t *indices /*nnz*/,
+                         const int32_t *indptr /*n_seg+1*/, int K, int n_seg, int n_nb, int nnz, int F,
+                         int req, const void *plan, int plan_chunk, float *partial, sg_stream_t stream);
+
+/* A3  data-gradient of seg_weighted_pool
+ * replaces _backward_seg_take_k_corr_embed2 -> SegTakeKCorrBackwardEmbed2Impl<gpu>
+ * (seg_op.cc:700-712, seg_op.cu:981-1006, compute_grad_embed2 seg_op.cu:882-926)
+ *   gdata[k, indices[p], :] (=|+=) weights[k,p] * gout[k, seg(p), :]
+ * computed as a gather over the transposed pattern (no atomics, no per-call sort).
+ * `t_plan` is a plan built on t_indptr (or NULL). */
+int sg_weighted_pool_bwd_data(float *gdata /*K,n_nb,F*/, const float *gout /*K,n_seg,F*/,
+                              const float *weights /*K,nnz*/, const int32_t *t_indptr,
+                              const int32_t *t_perm, const int32_t *t_seg, int K, int n_seg, int n_nb,
+                              int nnz, int F, int req, const void *t_plan, int plan_chunk, float *partial,
+                              sg_stream_t stream);
+
+/* A4  seg_take_k_corr (inner product) = weight-gradient of seg_weighted_pool
+ * replaces SegTakeKCorrImpl<gpu> (seg_op.cu:928-954, kernel seg_op.cu:573-664)
+ *   dst[k,p] (=|+=) <embed1[k, seg(p), :], embed2[k, indices[p], :]> */
+int sg_take_k_corr(float *dst /*K,nnz*/, const float *embed1 /*K,n_node,F*/,
+                   const float *embed2 /*K,n_nb,F*/, const int32_t *indices, const int32_t *indptr,
+                   int K, int n_node, int n_nb, int nnz, int F, int req, sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A5  seg_pool (sum | mean | max+argmax) forward / backward
+ * replaces SegPoolForward / SegSumMeanPoolBackward / SegMaxPoolBackward
+ * (seg_op.h:542-619, seg_op.cu:1057-1135,1171-1215,1286-1350)
+ * argmax holds the POSITION p on the nnz axis (seg_op.cc:282), -1 for an empty segment
+ * whose value is 0; ties keep the first position.  Forward has no ADD mode (seg_op.cc:252).
+ * ---------------------------------------------------------------------------------------- */
+int sg_seg_pool_fwd(float *dst /*B,n_seg,F*/, int32_t *argmax /*B,n_seg,F or NULL*/,
+                    const float *data /*B,n_nb,F*/, const int32_t *indices, const int32_t *indptr,
+                    int B, int n_seg, int n_nb, int nnz, int F, int pool_type, const void *plan,
+                    int plan_chunk, float *partial, sg_stream_t stream);
+int sg_seg_pool_bwd(float *gdata /*B,n_nb,F*/, const float *gout /*B,n_seg,F*/,
+                    const int32_t *argmax /*max only*/, const int32_t *indptr, const int32_t *t_indptr,
+                    const int32_t *t_perm, const int32_t *t_seg, int B, int n_seg, int n_nb, int nnz,
+                    int F, int pool_type, int req, const void *t_plan, int plan_chunk, float *partial,
+                    sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A6  contiguous segment ops over a (B, nnz) array
+ * replaces SegReduceImpl<gpu> (seg_op.cu:174-269) and SegBroadcastBinaryImpl<gpu>
+ * (seg_op.cu:282-330); seg_sum's gradient is SG_BCAST_TO (seg_op.cc:370-379)
+ * ---------------------------------------------------------------------------------------- */
+int sg_seg_reduce(float *dst /*B,n_seg*/, const float *data /*B,nnz*/, const int32_t *indptr, int B,
+                  int nnz, int n_seg, int reduce_type, int req, sg_stream_t stream);
+int sg_seg_broadcast_binary(float *dst /*B,nnz*/, const float *lhs /*B,nnz or NULL for TO*/,
+                            const float *rhs /*B,n_seg*/, const int32_t *indptr, int B, int nnz,
+                            int n_seg, int op, int req, sg_stream_t stream);
+/* seg_softmax forward/backward (seg_op.cu:385-513) — one fused kernel each. */
+int sg_seg_softmax_fwd(float *dst, const float *data, const int32_t *indptr, int B, int nnz, int n_seg,
+                       sg_stream_t stream);
+int sg_seg_softmax_bwd(float *dst, const float *ograd, const float *val, const int32_t *indptr, int B,
+                       int nnz, int n_seg, int req, sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  Fused multi-relation aggregation (all R rating levels in one launch, aggregate-first)
+ * replaces the per-level FullyConnected + seg_weighted_pool + add_n/concat loop of
+ * MultiLinkGCNAggregator.hybrid_forward (mxgraph/layers/aggregators.py:133-159), using
+ *   sum_p s[p] (W_r x[e[p]] + b_r) = W_r (sum_p s[p] x[e[p]]) + b_r sum_p s[p].
+ * The R CSRs are concatenated relation-major: segment id = r * n_dst + i.
+ *   agg [n_dst, R*D]   agg[i, r*D:(r+1)*D] = sum_{p in seg(r,i)} support[p] * x[end_points[p], :]
+ *   wsum[n_dst, R]     wsum[i, r]          = sum_{p in seg(r,i)} support[p]
+ * Backward (data-gradient): the same gather over the transposed pattern, reading
+ * gagg viewed as [(n_dst*R), D] rows:  gx[n,:] = sum_q t_w[q] * gagg_row[t_src[q]].
+ * ---------------------------------------------------------------------------------------- */
+int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x /*n_nb,D*/,
+                         const float *support /*nnz*/, const int32_t *end_points /*nnz*/,
+                         const int32_t *cat_indptr /*R*n_dst+1*/, int R, int n_dst, int n_nb, int nnz,
+                         int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream);
+/* Per-plan preparation of the transposed operands from sg_csr_transpose() outputs:
+ *   t_src[q] = i*R + r  for the segment s = r*n_dst + i owning position t_perm[q]
+ *   t_w[q]   = support[t_perm[q]] */
+int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_perm,
+                                  const int32_t *t_seg, const float *support, int R, int n_dst, int nnz,
+                                  sg_stream_t stream);
+int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, const float *t_w,
+                         const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
+                         int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,
+                         sg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARGCN_B200_H_ */

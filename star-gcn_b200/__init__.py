@@ -1,0 +1,14 @@
+"""stargcn_b200 — Blackwell-native hot path of STAR-GCN.
+
+The package directory is ``star-gcn_b200/``; it is importable as ``stargcn_b200`` through
+the one-file shim ``stargcn_b200.py`` at the repo root.
+
+    seg_op     the eight ``mx.nd.contrib.seg_*`` operators of the reference on torch tensors
+    layers     mirror of ``mxgraph.layers`` (aggregators, HeterGCNLayer, StackedHeterGCNLayers)
+    graph      device-resident multi-relation CSR plans + the fused aggregation op
+    decoder    masked-embedding lookup, reconstruction decoder and losses
+"""
+from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
+from . import seg_op, graph, layers  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,91 @@
+// Shared helpers for libstargcn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/stargcn_b200.h"
+
+namespace sg {
+
+// ---- thread-local error string + launch counter (the only state the library keeps) ----
+char *err_buf();
+void count_launch(int n = 1);
+int fail(int code, const char *fmt, ...);
+
+#define SG_REQUIRE(cond, ...)                                      \
+  do {                                                             \
+    if (!(cond)) return ::sg::fail(SG_ERR_INVALID, __VA_ARGS__);   \
+  } while (0)
+
+#define SG_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return ::sg::fail(SG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+  } while (0)
+
+// Checks the launch that was just enqueued (no synchronisation).
+#define SG_LAUNCHED(name)                                                                      \
+  do {                                                                                         \
+    ::sg::count_launch();                                                                      \
+    cudaError_t e__ = cudaPeekAtLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::sg::fail(SG_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+inline bool valid_req(int req) { return req == SG_REQ_NULL || req == SG_REQ_WRITE || req == SG_REQ_ADD; }
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// ---- segment schedule ("plan") layout, shared by plan.cu and the gather kernels ----
+// One work item = a run of at most `chunk` consecutive edges of one segment.
+//   x: first edge, y: one-past-last edge, z: segment id, w: partial slot (-1: writes the output)
+struct PlanHeader {
+  int n_items;     // written by the build kernels
+  int n_long;      // segments cut into > 1 item
+  int n_partials;  // partial rows in use
+  int chunk;
+  int n_seg;
+  int nnz;
+  int cap_items;
+  int cap_long;
+};
+// {segment, first partial slot, number of partials, unused}
+struct PlanView {
+  const PlanHeader *hdr;
+  const int4 *items;
+  const int4 *longs;
+};
+
+inline size_t plan_cap_items(int n_seg, int nnz, int chunk) { return (size_t)n_seg + (size_t)nnz / chunk + 1; }
+inline size_t plan_cap_long(int nnz, int chunk) { return (size_t)nnz / chunk + 1; }
+inline size_t plan_off_items() { return 64; }
+inline size_t plan_off_longs(int n_seg, int nnz, int chunk) {
+  return plan_off_items() + align_up(plan_cap_items(n_seg, nnz, chunk) * sizeof(int4), 64);
+}
+inline size_t plan_off_scan(int n_seg, int nnz, int chunk) {
+  return plan_off_longs(n_seg, nnz, chunk) + align_up(plan_cap_long(nnz, chunk) * sizeof(int4), 64);
+}
+
+// exclusive scan of n int32 (out may alias in); ws needs scan_ws_bytes(n)
+size_t scan_ws_bytes(int n);
+int exclusive_scan_i32(int32_t *out, const int32_t *in, int n, int32_t *total /*device, may be null*/,
+                       void *ws, cudaStream_t stream);
+
+}  // namespace sg

@@ -1,0 +1,300 @@
+// The hot kernel: CSR weighted gather-accumulate
+//     out[seg, :] (=|+=) sum_{p in seg} w[p] * src[idx[p], :]
+// used for seg_weighted_pool forward (A2), its data-gradient over the transposed pattern (A3),
+// seg_pool sum/mean (A5) and the fused multi-relation aggregation forward/backward (A1).
+//
+// Mapping (HBM/L2-bandwidth bound, ~0.5 flop per gathered byte, so no tensor cores here):
+//   * a GROUP of LPR lanes owns one work item (a run of <= chunk edges of one segment) and
+//     covers one source row with 16-byte loads: for D=64 a row is 256 B = 16 lanes x float4,
+//     so a warp keeps two independent items in flight and every row load is one fully
+//     used 128-B line pair
+//   * UNROLL independent row loads are issued before any FMA (memory-level parallelism)
+//   * heavy-tailed degree distributions are balanced by the plan (plan.cu): long segments are
+//     cut into chunks whose partial rows are combined by a second, tiny kernel in a fixed
+//     order -> no float atomics, bit-identical results run to run (the reference also avoids
+//     atomics: seg_op.cu:747-790)
+// Reference kernels replaced: SegTakeKCorrBackwardEmbed1Kernel (seg_op.cu:682-722),
+// SegTakeKCorrBackwardEmbed2Kernel (seg_op.cu:747-790), SegPoolKernel sum/mean
+// (seg_op.cu:1057-1135), SegPoolBackwardKernel sum/mean (seg_op.cu:1171-1215).
+#include "common.cuh"
+#include "gather.cuh"
+
+namespace sg {
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VEC>
+__device__ __forceinline__ void ld_row(float (&v)[VEC], const float *p) {
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void ld_plain(float (&v)[VEC], const float *p) {
+  if constexpr (VEC == 4) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = *reinterpret_cast<const float2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = *p;
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_row(float *p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if constexpr (VEC == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+  else *p = v[0];
+}
+
+__device__ __forceinline__ long long out_offset(const GatherArgs &a, int seg) {
+  if (a.n_out_rows == a.n_seg) return (long long)seg * a.ld_out;
+  int r = seg / a.n_out_rows, i = seg - r * a.n_out_rows;
+  return (long long)i * a.ld_out + (long long)r * a.F;
+}
+
+template <int VEC, int LPR, int NV, int UNROLL>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int n_groups = (gridDim.x * blockDim.x) / LPR;
+  const int k = blockIdx.y;
+  const int col0 = blockIdx.z * (LPR * NV * VEC);  // column chunk for very wide rows
+
+  const float *__restrict__ src = a.src + (long long)k * a.src_batch_stride;
+  const float *__restrict__ w = a.w ? a.w + (long long)k * a.w_batch_stride : nullptr;
+  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
+  float *__restrict__ partial = a.partial ? a.partial + (long long)k * a.partial_batch_stride : nullptr;
+  const int32_t *__restrict__ idx = a.idx;
+  const int32_t *__restrict__ perm = a.perm;
+
+  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
+
+  for (int it = group; it < n_items; it += n_groups) {
+    int4 d;
+    if (a.hdr) {
+      d = __ldg(a.items + it);
+    } else {
+      d = make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
+    }
+    float acc[NV][VEC];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[v][e] = 0.f;
+    float wacc = 0.f;
+
+    for (int p = d.x; p < d.y; p += UNROLL) {
+      int id[UNROLL];
+      float wv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const bool ok = p + u < d.y;
+        id[u] = ok ? __ldg(idx + p + u) : -1;
+        wv[u] = 1.f;
+        if (w) wv[u] = ok ? (perm ? __ldg(w + __ldg(perm + p + u)) : __ldg(w + p + u)) : 0.f;
+        if (a.inv_len_indptr && ok)
+          wv[u] = 1.f / (float)(__ldg(a.inv_len_indptr + id[u] + 1) - __ldg(a.inv_len_indptr + id[u]));
+      }
+      float val[UNROLL][NV][VEC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = col0 + (v * LPR + lane) * VEC;
+          if (id[u] >= 0 && c < a.F) {
+            ld_row<VEC>(val[u][v], src + (long long)id[u] * a.ld_src + c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) val[u][v][e] = 0.f;
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (id[u] >= 0) {
+          wacc += wv[u];
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[v][e] = fmaf(wv[u], val[u][v][e], acc[v][e]);
+        }
+      }
+    }
+
+    if (d.w >= 0) {  // piece of a split segment: park the partial row
+      float *prow = partial + (long long)d.w * a.F;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = col0 + (v * LPR + lane) * VEC;
+        if (c < a.F) st_row<VEC>(prow + c, acc[v]);
+      }
+      if (a.partial_wsum && lane == 0 && blockIdx.z == 0) a.partial_wsum[d.w] = wacc;
+    } else {
+      float *orow = out + out_offset(a, d.z);
+      const float inv = a.mean && d.y > d.x ? 1.f / (float)(d.y - d.x) : 1.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = col0 + (v * LPR + lane) * VEC;
+        if (c < a.F) {
+          float r[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) r[e] = a.mean ? acc[v][e] * inv : acc[v][e];
+          if (a.req == SG_REQ_ADD) {
+            float o[VEC];
+            ld_plain<VEC>(o, orow + c);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) r[e] += o[e];
+          }
+          st_row<VEC>(orow + c, r);
+        }
+      }
+      if (a.wsum && lane == 0 && blockIdx.z == 0) {
+        // wsum is [n_out_rows, R] with R = n_seg / n_out_rows
+        int r = d.z / a.n_out_rows, i = d.z - r * a.n_out_rows;
+        a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
+      }
+    }
+  }
+}
+
+// Second pass: fixed-order sum of the partial rows of every split segment.
+template <int VEC, int LPR, int NV>
+__global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int n_groups = (gridDim.x * blockDim.x) / LPR;
+  const int k = blockIdx.y;
+  const int col0 = blockIdx.z * (LPR * NV * VEC);
+  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
+  const float *__restrict__ partial = a.partial + (long long)k * a.partial_batch_stride;
+  const int n_long = a.hdr->n_long;
+  for (int li = group; li < n_long; li += n_groups) {
+    const int4 d = __ldg(a.longs + li);  // {segment, first slot, count}
+    float acc[NV][VEC];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[v][e] = 0.f;
+    float wacc = 0.f;
+    for (int s = 0; s < d.z; ++s) {
+      const float *prow = partial + (long long)(d.y + s) * a.F;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = col0 + (v * LPR + lane) * VEC;
+        if (c < a.F) {
+          float t[VEC];
+          ld_plain<VEC>(t, prow + c);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[v][e] += t[e];
+        }
+      }
+      if (a.partial_wsum) wacc += a.partial_wsum[d.y + s];
+    }
+    float *orow = out + out_offset(a, d.x);
+    float inv = 1.f;
+    if (a.mean) {
+      const int len = __ldg(a.indptr + d.x + 1) - __ldg(a.indptr + d.x);
+      inv = 1.f / (float)len;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = col0 + (v * LPR + lane) * VEC;
+      if (c < a.F) {
+        float r[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) r[e] = a.mean ? acc[v][e] * inv : acc[v][e];
+        if (a.req == SG_REQ_ADD) {
+          float o[VEC];
+          ld_plain<VEC>(o, orow + c);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) r[e] += o[e];
+        }
+        st_row<VEC>(orow + c, r);
+      }
+    }
+    if (a.wsum && lane == 0 && blockIdx.z == 0) {
+      int r = d.x / a.n_out_rows, i = d.x - r * a.n_out_rows;
+      a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
+    }
+  }
+}
+
+template <int VEC, int LPR, int NV>
+static int launch_gather(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  constexpr int UNROLL = NV >= 2 ? 2 : 4;
+  constexpr int kThreads = 256;
+  constexpr int groups_per_block = kThreads / LPR;
+  const int col_chunks = ceil_div(a.F, LPR * NV * VEC);
+  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)K, (unsigned)col_chunks);
+  gather_rows_kernel<VEC, LPR, NV, UNROLL><<<grid, kThreads, 0, st>>>(a);
+  SG_LAUNCHED("gather_rows_kernel");
+  if (a.hdr && n_long_cap > 0) {
+    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
+    if (cb > cap) cb = cap;
+    dim3 cgrid((unsigned)cb, (unsigned)K, (unsigned)col_chunks);
+    combine_partials_kernel<VEC, LPR, NV><<<cgrid, kThreads, 0, st>>>(a);
+    SG_LAUNCHED("combine_partials_kernel");
+  }
+  return SG_OK;
+}
+
+template <int VEC>
+static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  const int vecs = ceil_div(a.F, VEC);
+  if (vecs <= 1) return launch_gather<VEC, 1, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 2) return launch_gather<VEC, 2, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 4) return launch_gather<VEC, 4, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 8) return launch_gather<VEC, 8, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 16) return launch_gather<VEC, 16, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 32) return launch_gather<VEC, 32, 1>(a, K, n_items_cap, n_long_cap, st);
+  if (vecs <= 64) return launch_gather<VEC, 32, 2>(a, K, n_items_cap, n_long_cap, st);
+  return launch_gather<VEC, 32, 4>(a, K, n_items_cap, n_long_cap, st);  // wider rows loop over blockIdx.z
+}
+
+static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
+  a.n_seg = n_seg;
+  int n_items_cap = n_seg, n_long_cap = 0;
+  if (plan) {
+    // header fields live on the device; size the grids from the host-side capacity bounds
+    SG_REQUIRE(aligned(plan, 16), "plan buffer must be 16-byte aligned");
+    SG_REQUIRE(a.plan_chunk > 0, "plan chunk must be given with a plan");
+    const char *base = static_cast<const char *>(plan);
+    a.hdr = reinterpret_cast<const PlanHeader *>(base);
+    a.items = reinterpret_cast<const int4 *>(base + plan_off_items());
+    a.longs = reinterpret_cast<const int4 *>(base + plan_off_longs(n_seg, nnz, a.plan_chunk));
+    n_items_cap = (int)plan_cap_items(n_seg, nnz, a.plan_chunk);
+    n_long_cap = (int)plan_cap_long(nnz, a.plan_chunk);
+    if (n_long_cap > 0) SG_REQUIRE(a.partial, "a plan with split segments needs a partial-row scratch buffer");
+  } else {
+    a.hdr = nullptr; a.items = nullptr; a.longs = nullptr; a.partial = nullptr; a.partial_wsum = nullptr;
+  }
+  if (n_seg == 0 || a.F == 0) return SG_OK;
+  const bool v4 = a.F % 4 == 0 && a.ld_src % 4 == 0 && a.ld_out % 4 == 0 && aligned(a.src, 16) && aligned(a.out, 16) &&
+                  (!a.partial || aligned(a.partial, 16)) && a.src_batch_stride % 4 == 0 && a.out_batch_stride % 4 == 0 &&
+                  a.partial_batch_stride % 4 == 0;
+  const bool v2 = a.F % 2 == 0 && a.ld_src % 2 == 0 && a.ld_out % 2 == 0 && aligned(a.src, 8) && aligned(a.out, 8) &&
+                  (!a.partial || aligned(a.partial, 8)) && a.src_batch_stride % 2 == 0 && a.out_batch_stride % 2 == 0 &&
+                  a.partial_batch_stride % 2 == 0;
+  if (v4) return dispatch_lpr<4>(a, K, n_items_cap, n_long_cap, st);
+  if (v2) return dispatch_lpr<2>(a, K, n_items_cap, n_long_cap, st);
+  return dispatch_lpr<1>(a, K, n_items_cap, n_long_cap, st);
+}
+
+}  // namespace sg

@@ -1,0 +1,361 @@
+// Segment bookkeeping: error state, int32 scan, segment ids, stable CSR transpose and the
+// work-item schedule ("plan") the gather kernels walk.  All integer work — bit-exact against
+// oracle/seg_ops_oracle.c (orc_seg_ids, orc_csr_transpose) and the reference's
+// gen_row_indices_by_indptr (GraphSampler/graph_sampler.cpp:378-391).
+#include <atomic>
+#include <cstdarg>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace sg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};  // process-wide: autograd runs backward on its own thread
+
+char *err_buf() { return g_err; }
+void count_launch(int n) { g_launches += n; }
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan (3 launches; n <= 2^31).  2048 elements per 256-thread block.
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// inclusive scan of one value per thread across a 256-thread block; returns inclusive value,
+// *block_total gets the sum.
+__device__ __forceinline__ int block_incl_scan(int v, int *block_total) {
+  __shared__ int warp_sums[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = warp_incl_scan(v, lane);
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+    s = warp_incl_scan(s, lane);
+    if (lane < kScanThreads / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  if (wid > 0) inc += warp_sums[wid - 1];
+  *block_total = warp_sums[kScanThreads / 32 - 1];
+  __syncthreads();
+  return inc;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t *__restrict__ in, int n,
+                                                               int32_t *__restrict__ tile_sums) {
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i)
+    if (base + i < n) s += in[base + i];
+  int total;
+  block_incl_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_of_tile_sums(int32_t *tile_sums, int n_tiles,
+                                                                  int32_t *total_out) {
+  int carry = 0;
+  for (int base = 0; base < n_tiles; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int v = i < n_tiles ? tile_sums[i] : 0;
+    int total;
+    int inc = block_incl_scan(v, &total);
+    if (i < n_tiles) tile_sums[i] = carry + inc - v;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply(int32_t *out, const int32_t *in, int n,
+                                                           const int32_t *__restrict__ tile_offs) {
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  int v[kScanPerThread];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    s += v[i];
+  }
+  int total;
+  int run = block_incl_scan(s, &total) - s + tile_offs[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+}
+
+size_t scan_ws_bytes(int n) { return align_up((size_t)(ceil_div(n > 0 ? n : 1, kScanTile)) * sizeof(int32_t), 64); }
+
+int exclusive_scan_i32(int32_t *out, const int32_t *in, int n, int32_t *total, void *ws, cudaStream_t st) {
+  if (n <= 0) {
+    if (total) SG_CUDA(cudaMemsetAsync(total, 0, sizeof(int32_t), st));
+    return SG_OK;
+  }
+  int32_t *tile_sums = static_cast<int32_t *>(ws);
+  const int tiles = ceil_div(n, kScanTile);
+  scan_tile_sums<<<tiles, kScanThreads, 0, st>>>(in, n, tile_sums);
+  SG_LAUNCHED("scan_tile_sums");
+  scan_of_tile_sums<<<1, kScanThreads, 0, st>>>(tile_sums, tiles, total);
+  SG_LAUNCHED("scan_of_tile_sums");
+  scan_apply<<<tiles, kScanThreads, 0, st>>>(out, in, n, tile_sums);
+  SG_LAUNCHED("scan_apply");
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// segment ids: position p -> the segment s with indptr[s] <= p < indptr[s+1]
+// (upper_bound over indptr, so runs of empty segments are skipped correctly)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int seg_of_pos(const int32_t *__restrict__ indptr, int n_seg, int p) {
+  int lo = 0, hi = n_seg;  // find first s with indptr[s+1] > p
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(indptr + mid + 1) > p) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) seg_ids_kernel(int32_t *__restrict__ seg_ids,
+                                                      const int32_t *__restrict__ indptr, int n_seg, int nnz) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
+    seg_ids[p] = seg_of_pos(indptr, n_seg, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// plan build
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_count(const int32_t *__restrict__ indptr, int n_seg, int chunk,
+                                                  int32_t *__restrict__ c_item, int32_t *__restrict__ c_long,
+                                                  int32_t *__restrict__ c_part) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  int len = indptr[s + 1] - indptr[s];
+  int nch = len <= chunk ? 1 : ceil_div(len, chunk);
+  c_item[s] = nch;
+  c_long[s] = len > chunk;
+  c_part[s] = len > chunk ? nch : 0;
+}
+
+__global__ void __launch_bounds__(256) plan_fill(PlanHeader *hdr, int4 *__restrict__ items, int4 *__restrict__ longs,
+                                                 const int32_t *__restrict__ indptr, int n_seg, int nnz, int chunk,
+                                                 const int32_t *__restrict__ o_item, const int32_t *__restrict__ o_long,
+                                                 const int32_t *__restrict__ o_part, int cap_items, int cap_long) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) {
+    hdr->chunk = chunk; hdr->n_seg = n_seg; hdr->nnz = nnz; hdr->cap_items = cap_items; hdr->cap_long = cap_long;
+  }
+  if (s >= n_seg) return;
+  const int beg = indptr[s], end = indptr[s + 1], len = end - beg;
+  const int base = o_item[s];
+  if (len <= chunk) {
+    items[base] = make_int4(beg, end, s, -1);
+  } else {
+    const int nch = ceil_div(len, chunk), slot = o_part[s];
+    for (int c = 0; c < nch; ++c) {
+      int b = beg + c * chunk;
+      items[base + c] = make_int4(b, min(b + chunk, end), s, slot + c);
+    }
+    longs[o_long[s]] = make_int4(s, slot, nch, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// transpose helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iota_kernel(int32_t *__restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
+// t_indptr[n] = number of sorted keys < n  (lower_bound), n in [0, n_nb]
+__global__ void __launch_bounds__(256) indptr_from_sorted(int32_t *__restrict__ t_indptr,
+                                                          const int32_t *__restrict__ keys, int nnz, int n_nb) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > n_nb) return;
+  int lo = 0, hi = nnz;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(keys + mid) < n) lo = mid + 1; else hi = mid;
+  }
+  t_indptr[n] = lo;
+}
+
+__global__ void __launch_bounds__(256) gather_i32(int32_t *__restrict__ out, const int32_t *__restrict__ src,
+                                                  const int32_t *__restrict__ idx, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+
+__global__ void __launch_bounds__(256) multilink_finish(int32_t *__restrict__ t_src, float *__restrict__ t_w,
+                                                        const int32_t *__restrict__ t_perm,
+                                                        const int32_t *__restrict__ t_seg,
+                                                        const float *__restrict__ support, int R, int n_dst, int nnz) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * blockDim.x) {
+    int s = t_seg[q];
+    int r = s / n_dst, i = s - r * n_dst;
+    t_src[q] = i * R + r;
+    t_w[q] = support[t_perm[q]];
+  }
+}
+
+static inline int grid_for(long long n, int threads = 256) {
+  long long g = ceil_div<long long>(n > 0 ? n : 1, threads);
+  long long cap = (long long)num_sms() * 32;
+  return (int)(g < cap ? g : cap);
+}
+
+static int key_bits(int n_nb) {
+  int bits = 1;
+  while (bits < 31 && (1LL << bits) < (long long)n_nb) ++bits;
+  return bits;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+const char *sg_last_error(void) { return sg::err_buf(); }
+int sg_abi_version(void) { return 1; }
+long long sg_launch_count(void) { return sg::g_launches.load(); }
+void sg_launch_count_reset(void) { sg::g_launches.store(0); }
+
+int sg_seg_ids(int32_t *seg_ids, const int32_t *indptr, int n_seg, int nnz, sg_stream_t stream) {
+  SG_REQUIRE(n_seg >= 0 && nnz >= 0, "sg_seg_ids: negative size (n_seg=%d nnz=%d)", n_seg, nnz);
+  if (nnz == 0) return SG_OK;
+  SG_REQUIRE(seg_ids && indptr, "sg_seg_ids: null pointer");
+  seg_ids_kernel<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(seg_ids, indptr, n_seg, nnz);
+  SG_LAUNCHED("seg_ids_kernel");
+  return SG_OK;
+}
+
+size_t sg_csr_transpose_ws_bytes(int n_seg, int n_nb, int nnz) {
+  (void)n_seg;
+  if (nnz <= 0) return 64;
+  size_t cub_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                                  (const int32_t *)nullptr, (int32_t *)nullptr, nnz, 0,
+                                                  key_bits(n_nb));
+  if (e != cudaSuccess) {
+    sg::fail(SG_ERR_CUDA, "sg_csr_transpose_ws_bytes: CUB size query failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return 0;
+  }
+  // sorted keys + iota + seg ids + CUB scratch
+  return 3 * align_up((size_t)nnz * sizeof(int32_t), 256) + align_up(cub_bytes, 256) + 256;
+}
+
+int sg_csr_transpose(int32_t *t_indptr, int32_t *t_perm, int32_t *t_seg, const int32_t *indices,
+                     const int32_t *indptr, int n_seg, int n_nb, int nnz, void *ws, size_t ws_bytes,
+                     sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(n_seg >= 0 && n_nb >= 0 && nnz >= 0, "sg_csr_transpose: negative size");
+  SG_REQUIRE(t_indptr, "sg_csr_transpose: null t_indptr");
+  if (nnz == 0) {
+    SG_CUDA(cudaMemsetAsync(t_indptr, 0, sizeof(int32_t) * (size_t)(n_nb + 1), st));
+    return SG_OK;
+  }
+  SG_REQUIRE(t_perm && t_seg && indices && indptr && ws, "sg_csr_transpose: null pointer");
+  const size_t need = sg_csr_transpose_ws_bytes(n_seg, n_nb, nnz);
+  if (need == 0) return SG_ERR_CUDA;
+  if (ws_bytes < need) return sg::fail(SG_ERR_WORKSPACE, "sg_csr_transpose: workspace %zu < %zu bytes", ws_bytes, need);
+  const size_t stride = align_up((size_t)nnz * sizeof(int32_t), 256);
+  char *base = static_cast<char *>(ws);
+  int32_t *keys_sorted = reinterpret_cast<int32_t *>(base);
+  int32_t *iota = reinterpret_cast<int32_t *>(base + stride);
+  int32_t *seg_ids = reinterpret_cast<int32_t *>(base + 2 * stride);
+  void *cub_ws = base + 3 * stride;
+  size_t cub_bytes = ws_bytes - 3 * stride;
+
+  iota_kernel<<<grid_for(nnz), 256, 0, st>>>(iota, nnz);
+  SG_LAUNCHED("iota_kernel");
+  seg_ids_kernel<<<grid_for(nnz), 256, 0, st>>>(seg_ids, indptr, n_seg, nnz);
+  SG_LAUNCHED("seg_ids_kernel");
+  // LSD radix sort is stable: equal destinations keep ascending original position.
+  SG_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, indices, keys_sorted, (const int32_t *)iota, t_perm, nnz,
+                                          0, key_bits(n_nb), st));
+  sg::count_launch(4);
+  indptr_from_sorted<<<ceil_div(n_nb + 1, 256), 256, 0, st>>>(t_indptr, keys_sorted, nnz, n_nb);
+  SG_LAUNCHED("indptr_from_sorted");
+  gather_i32<<<grid_for(nnz), 256, 0, st>>>(t_seg, seg_ids, t_perm, nnz);
+  SG_LAUNCHED("gather_i32");
+  return SG_OK;
+}
+
+size_t sg_plan_bytes(int n_seg, int nnz, int chunk) {
+  if (n_seg < 0 || nnz < 0 || chunk <= 0) return 0;
+  return plan_off_scan(n_seg, nnz, chunk) + 3 * align_up((size_t)(n_seg + 1) * sizeof(int32_t), 64) +
+         scan_ws_bytes(n_seg) + 64;
+}
+
+size_t sg_plan_partial_rows(int n_seg, int nnz, int chunk) {
+  (void)n_seg;
+  if (nnz < 0 || chunk <= 0) return 0;
+  // a segment is split only if len > chunk, and then into ceil(len/chunk) <= 2*len/chunk rows
+  return 2 * ((size_t)nnz / chunk) + 1;
+}
+
+int sg_plan_build(void *plan, size_t plan_bytes, const int32_t *indptr, int n_seg, int nnz, int chunk,
+                  sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(plan && indptr, "sg_plan_build: null pointer");
+  SG_REQUIRE(n_seg >= 0 && nnz >= 0 && chunk > 0, "sg_plan_build: bad sizes (n_seg=%d nnz=%d chunk=%d)", n_seg, nnz, chunk);
+  SG_REQUIRE((reinterpret_cast<uintptr_t>(plan) & 15) == 0, "sg_plan_build: plan buffer must be 16-byte aligned");
+  const size_t need = sg_plan_bytes(n_seg, nnz, chunk);
+  if (plan_bytes < need) return sg::fail(SG_ERR_WORKSPACE, "sg_plan_build: plan buffer %zu < %zu bytes", plan_bytes, need);
+  char *base = static_cast<char *>(plan);
+  PlanHeader *hdr = reinterpret_cast<PlanHeader *>(base);
+  int4 *items = reinterpret_cast<int4 *>(base + plan_off_items());
+  int4 *longs = reinterpret_cast<int4 *>(base + plan_off_longs(n_seg, nnz, chunk));
+  const size_t arr = align_up((size_t)(n_seg + 1) * sizeof(int32_t), 64);
+  char *scan_base = base + plan_off_scan(n_seg, nnz, chunk);
+  int32_t *a_item = reinterpret_cast<int32_t *>(scan_base);
+  int32_t *a_long = reinterpret_cast<int32_t *>(scan_base + arr);
+  int32_t *a_part = reinterpret_cast<int32_t *>(scan_base + 2 * arr);
+  void *scan_ws = scan_base + 3 * arr;
+  SG_CUDA(cudaMemsetAsync(hdr, 0, sizeof(PlanHeader), st));
+  if (n_seg == 0) return SG_OK;
+  const int g = ceil_div(n_seg, 256);
+  plan_count<<<g, 256, 0, st>>>(indptr, n_seg, chunk, a_item, a_long, a_part);
+  SG_LAUNCHED("plan_count");
+  int rc;
+  if ((rc = exclusive_scan_i32(a_item, a_item, n_seg, &hdr->n_items, scan_ws, st)) != SG_OK) return rc;
+  if ((rc = exclusive_scan_i32(a_long, a_long, n_seg, &hdr->n_long, scan_ws, st)) != SG_OK) return rc;
+  if ((rc = exclusive_scan_i32(a_part, a_part, n_seg, &hdr->n_partials, scan_ws, st)) != SG_OK) return rc;
+  plan_fill<<<g, 256, 0, st>>>(hdr, items, longs, indptr, n_seg, nnz, chunk, a_item, a_long, a_part,
+                               (int)plan_cap_items(n_seg, nnz, chunk), (int)plan_cap_long(nnz, chunk));
+  SG_LAUNCHED("plan_fill");
+  return SG_OK;
+}
+
+int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_perm, const int32_t *t_seg,
+                                  const float *support, int R, int n_dst, int nnz, sg_stream_t stream) {
+  SG_REQUIRE(R > 0 && n_dst >= 0 && nnz >= 0, "sg_multilink_transpose_finish: bad sizes");
+  if (nnz == 0) return SG_OK;
+  SG_REQUIRE(t_src && t_w && t_perm && t_seg && support, "sg_multilink_transpose_finish: null pointer");
+  multilink_finish<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(t_src, t_w, t_perm, t_seg, support, R, n_dst, nnz);
+  SG_LAUNCHED("multilink_finish");
+  return SG_OK;
+}
+
+}  // extern "C"
