@@ -169,6 +169,109 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fast path: rows of exactly LPR*4 floats (F in {16,32,64,128}), every per-call option a
+// template parameter so the edge loop is  idx/w loads -> address -> LDG.128 -> 4 FFMA  and
+// nothing else (the generic kernel above spends ~50 issued instructions per edge on runtime
+// option checks; this one ~8).  Full UNROLL-edge batches run unpredicated; one predicated
+// batch handles the tail.
+//   WMODE 0: weight 1   1: w[p]   2: w[perm[p]]   3: 1/len(segment idx[p]) (avg-pool backward)
+// ------------------------------------------------------------------------------------------
+template <int WMODE>
+__device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *__restrict__ w, int p, int id) {
+  if constexpr (WMODE == 0) return 1.f;
+  else if constexpr (WMODE == 1) return __ldg(w + p);
+  else if constexpr (WMODE == 2) return __ldg(w + __ldg(a.perm + p));
+  else return 1.f / (float)(__ldg(a.inv_len_indptr + id + 1) - __ldg(a.inv_len_indptr + id));
+}
+
+template <int LPR, int UNROLL, int WMODE, bool WSUM>
+__global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs a) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int n_groups = (gridDim.x * blockDim.x) / LPR;
+  const int k = blockIdx.y;
+
+  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src + (long long)k * a.src_batch_stride) + lane;
+  const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
+  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
+  const int32_t *__restrict__ idx = a.idx;
+  const int ld4 = a.ld_src >> 2;
+  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
+
+  for (int it = group; it < n_items; it += n_groups) {
+    int4 d;
+    if (a.hdr) d = __ldg(a.items + it);
+    else d = make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wacc = 0.f;
+    int p = d.x;
+    for (; p + UNROLL <= d.y; p += UNROLL) {
+      int id[UNROLL];
+      float wv[UNROLL];
+      float4 val[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) id[u] = __ldg(idx + p + u);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) val[u] = __ldg(src + (long long)id[u] * ld4);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) wv[u] = edge_weight<WMODE>(a, w, p + u, id[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if constexpr (WSUM) wacc += wv[u];
+        acc.x = fmaf(wv[u], val[u].x, acc.x);
+        acc.y = fmaf(wv[u], val[u].y, acc.y);
+        acc.z = fmaf(wv[u], val[u].z, acc.z);
+        acc.w = fmaf(wv[u], val[u].w, acc.w);
+      }
+    }
+    if (p < d.y) {  // tail: one predicated batch
+      int id[UNROLL];
+      float wv[UNROLL];
+      float4 val[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u) id[u] = p + u < d.y ? __ldg(idx + p + u) : -1;
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u)
+        val[u] = id[u] >= 0 ? __ldg(src + (long long)id[u] * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u) wv[u] = id[u] >= 0 ? edge_weight<WMODE>(a, w, p + u, id[u]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < UNROLL - 1; ++u) {
+        if (id[u] >= 0) {  // keeps the addition order of the serial loop and never touches a masked row
+          if constexpr (WSUM) wacc += wv[u];
+          acc.x = fmaf(wv[u], val[u].x, acc.x);
+          acc.y = fmaf(wv[u], val[u].y, acc.y);
+          acc.z = fmaf(wv[u], val[u].z, acc.z);
+          acc.w = fmaf(wv[u], val[u].w, acc.w);
+        }
+      }
+    }
+
+    if (d.w >= 0) {  // piece of a split segment: park the partial row
+      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * (LPR * 4);
+      reinterpret_cast<float4 *>(prow)[lane] = acc;
+      if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
+    } else {
+      float *orow = out + out_offset(a, d.z);
+      if (a.mean && d.y > d.x) {
+        const float inv = 1.f / (float)(d.y - d.x);
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      }
+      if (a.req == SG_REQ_ADD) {
+        const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      reinterpret_cast<float4 *>(orow)[lane] = acc;
+      if (WSUM && lane == 0) {
+        int r = d.z / a.n_out_rows, i = d.z - r * a.n_out_rows;
+        a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
+      }
+    }
+  }
+}
+
 // Second pass: fixed-order sum of the partial rows of every split segment.
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
@@ -268,6 +371,36 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+template <int LPR, int WMODE, bool WSUM>
+static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  constexpr int UNROLL = 8;
+  constexpr int kThreads = 256;
+  constexpr int groups_per_block = kThreads / LPR;
+  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)K, 1);
+  gather_rows_fast_kernel<LPR, UNROLL, WMODE, WSUM><<<grid, kThreads, 0, st>>>(a);
+  SG_LAUNCHED("gather_rows_fast_kernel");
+  if (a.hdr && n_long_cap > 0) {
+    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
+    if (cb > cap) cb = cap;
+    dim3 cgrid((unsigned)cb, (unsigned)K, 1);
+    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
+    SG_LAUNCHED("combine_partials_kernel");
+  }
+  return SG_OK;
+}
+
+template <int LPR>
+static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  if (a.inv_len_indptr) return launch_fast<LPR, 3, false>(a, K, n_items_cap, n_long_cap, st);
+  if (!a.w) return launch_fast<LPR, 0, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.perm) return launch_fast<LPR, 2, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.wsum) return launch_fast<LPR, 1, true>(a, K, n_items_cap, n_long_cap, st);
+  return launch_fast<LPR, 1, false>(a, K, n_items_cap, n_long_cap, st);
+}
+
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
   a.n_seg = n_seg;
   int n_items_cap = n_seg, n_long_cap = 0;
@@ -292,6 +425,15 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
   const bool v2 = a.F % 2 == 0 && a.ld_src % 2 == 0 && a.ld_out % 2 == 0 && aligned(a.src, 8) && aligned(a.out, 8) &&
                   (!a.partial || aligned(a.partial, 8)) && a.src_batch_stride % 2 == 0 && a.out_batch_stride % 2 == 0 &&
                   a.partial_batch_stride % 2 == 0;
+  if (v4 && a.ld_src == a.F && (!a.wsum || (a.w && !a.perm && !a.inv_len_indptr))) {  // exact-width fast path
+    switch (a.F) {
+      case 16: return dispatch_fast_mode<4>(a, K, n_items_cap, n_long_cap, st);
+      case 32: return dispatch_fast_mode<8>(a, K, n_items_cap, n_long_cap, st);
+      case 64: return dispatch_fast_mode<16>(a, K, n_items_cap, n_long_cap, st);
+      case 128: return dispatch_fast_mode<32>(a, K, n_items_cap, n_long_cap, st);
+      default: break;
+    }
+  }
   if (v4) return dispatch_lpr<4>(a, K, n_items_cap, n_long_cap, st);
   if (v2) return dispatch_lpr<2>(a, K, n_items_cap, n_long_cap, st);
   return dispatch_lpr<1>(a, K, n_items_cap, n_long_cap, st);

@@ -41,6 +41,18 @@ def small_problem(seed, n_dst, n_nb, nnz, R, D, U, accum, empty_level=False):
     return x, ws, bs, ep_l, ptr_l, sup_l, gout
 
 
+def pin_kink(pre, out_gpu, band=1e-5):
+    """LeakyReLU/ReLU have a gradient jump at pre == 0.  A pre-activation whose magnitude is inside
+    the fp32 rounding band of the sum (|pre| <= band * max|pre|) can land on either side of 0
+    depending on summation order — the reference's own fp32 result flips sign against its fp64
+    evaluation at such points — so the gradient oracle is evaluated with the branch the GPU forward
+    took there (sign(out) == sign(pre) for every activation used).  Everything outside the band is
+    untouched; the count of pinned entries is asserted to stay tiny."""
+    near = np.abs(pre) <= band * np.abs(pre).max()
+    assert (near & (pre != 0)).mean() < 1e-3   # exact zeros (empty segments) are not rounding cases
+    return np.where(near, np.where(out_gpu > 0, np.abs(pre) + 1e-30, -np.abs(pre) - 1e-30), pre).astype(pre.dtype)
+
+
 def build_agg(ws, bs, R, U, accum, act, ordinal):
     from stargcn_b200.layers import MultiLinkGCNAggregator
     agg = MultiLinkGCNAggregator(units=U, num_links=R, act=act, dropout_rate=0.0, ordinal_sharing=ordinal,
@@ -61,12 +73,12 @@ def test_multilink_aggregator_matches_reference_order(accum, act, ordinal, empty
     x, ws, bs, ep_l, ptr_l, sup_l, gout = small_problem(1, 70, 45, 1500, R, D, U, accum, empty_level)
     ref_out, pre = orl.multilink_aggregator_forward(x, ws, bs, ep_l, ptr_l, sup_l, accum, act, ordinal)
     ref64, pre64 = orl.multilink_aggregator_forward(x, ws, bs, ep_l, ptr_l, sup_l, accum, act, ordinal, fp64=True)
-    gx_ref, gw_ref, gb_ref = orl.multilink_aggregator_backward(x, ws, bs, ep_l, ptr_l, sup_l, gout, pre, accum, act, ordinal)
-    gx64, gw64, gb64 = orl.multilink_aggregator_backward(x, ws, bs, ep_l, ptr_l, sup_l, gout, pre64, accum, act, ordinal, fp64=True)
-
     agg = build_agg(ws, bs, R, U, accum, act, ordinal)
     xd = dev(x).requires_grad_(True)
     out = agg(xd, [dev(e) for e in ep_l], [dev(p) for p in ptr_l], [dev(s) for s in sup_l])
+    pre, pre64 = pin_kink(pre, host(out)), pin_kink(pre64, host(out))
+    gx_ref, gw_ref, gb_ref = orl.multilink_aggregator_backward(x, ws, bs, ep_l, ptr_l, sup_l, gout, pre, accum, act, ordinal)
+    gx64, gw64, gb64 = orl.multilink_aggregator_backward(x, ws, bs, ep_l, ptr_l, sup_l, gout, pre64, accum, act, ordinal, fp64=True)
     assert out.shape == ref_out.shape
     assert rel_err(host(out), ref_out) <= TOL
     # never further from the exact (fp64) answer than the reference's own fp32 path + tolerance
@@ -151,11 +163,12 @@ def test_ml100k_shape_layer_vs_oracle():
         ep_l, ptr_l, sup_l, _ = d[side]
         gout = rs.normal(size=(n_dst, U)).astype(np.float32)
         ref_out, pre = orl.multilink_aggregator_forward(x_nb, ws, bs, ep_l, ptr_l, sup_l, "sum", "leaky")
-        gx_ref, gw_ref, gb_ref = orl.multilink_aggregator_backward(x_nb, ws, bs, ep_l, ptr_l, sup_l, gout, pre, "sum", "leaky")
         agg = build_agg(ws, bs, R, U, "sum", "leaky", False)
         xd = dev(x_nb).requires_grad_(True)
         out = agg(xd, ep_l, ptr_l, sup_l)
         assert rel_err(host(out), ref_out) <= TOL
+        gx_ref, gw_ref, gb_ref = orl.multilink_aggregator_backward(x_nb, ws, bs, ep_l, ptr_l, sup_l, gout,
+                                                                   pin_kink(pre, host(out)), "sum", "leaky")
         out.backward(dev(gout))
         assert rel_err(host(xd.grad), gx_ref) <= TOL
         assert rel_err(host(agg.weight3.grad), gw_ref[3]) <= TOL
