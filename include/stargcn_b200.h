@@ -155,6 +155,13 @@ int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x /*n_nb,D*/,
                          const float *support /*nnz*/, const int32_t *end_points /*nnz*/,
                          const int32_t *cat_indptr /*R*n_dst+1*/, int R, int n_dst, int n_nb, int nnz,
                          int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream);
+/* Same aggregation written as the pre-split A operand of sg_gemm_tf32x3: row i of agg_hi / agg_lo
+ * (ld_agg floats, ld_agg >= R*D + R, multiple of 4) holds the R aggregated D-vectors followed by the
+ * R support sums wsum[i, r] at column R*D + r, each value x stored as (tf32-exact hi, x - hi).
+ * Columns beyond R*D + R are not written.  D must be 16, 32, 64 or 128. */
+int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const float *x, const float *support,
+                               const int32_t *end_points, const int32_t *cat_indptr, int R, int n_dst, int n_nb,
+                               int nnz, int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream);
 /* Per-plan preparation of the transposed operands from sg_csr_transpose() outputs:
  *   t_src[q] = i*R + r  for the segment s = r*n_dst + i owning position t_perm[q]
  *   t_w[q]   = support[t_perm[q]] */
@@ -165,6 +172,31 @@ int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, 
                          const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
                          int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,
                          sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A1 (transform part)  fp32-accurate GEMM on tcgen05 tensor cores (3xTF32 split)
+ * replaces the R FullyConnected calls + add_n of aggregators.py:141-159 (cuBLAS sgemm inside
+ * MXNet) and their backward.  Operands arrive pre-split (x = hi + lo, sg_split_tf32):
+ *   mn_major == 0:  D[M,N] = A[M,K] . B[N,K]^T      A, B row-major, K contiguous (lda, ldb)
+ *   mn_major == 1:  D[M,N] = A[K,M]^T . B[K,N]      A, B row-major, M / N contiguous (reduction over rows)
+ * lda / ldb must be multiples of 4 floats and the operands 16-byte aligned (TMA).
+ * epilogue 0: store; 1: leaky-ReLU with `slope` (0 = ReLU, 1 = identity).
+ * splits > 1 partitions K over CTAs; partials go to split_ws (sg_gemm_split_ws_bytes) and are
+ * summed in a fixed order, so results are bit-identical run to run.
+ * ---------------------------------------------------------------------------------------- */
+size_t sg_gemm_split_ws_bytes(int M, int N, int splits);
+int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int lda, const float *B_hi,
+                   const float *B_lo, int ldb, int M, int N, int K, int mn_major, int epilogue, float slope,
+                   int splits, float *split_ws, sg_stream_t stream);
+/* hi = src with the 13 low mantissa bits cleared, lo = src - hi; optional transpose; the
+ * destination has ld_dst >= columns and its padding is zero-filled. */
+int sg_split_tf32(float *hi, float *lo, int ld_dst, const float *src, int rows, int cols, int ld_src,
+                  int transpose, sg_stream_t stream);
+/* gZ = gout * act'(Z) evaluated from the saved layer output (leaky slope; 0 = ReLU), written
+ * pre-split and padded to ldz columns: the A operand of both backward GEMMs
+ * (replaces MXNet's LeakyReLU backward, mxgraph/layers/common.py:46-47). */
+int sg_act_bwd_split(float *gz_hi, float *gz_lo, int ldz, const float *gout, const float *out, int M, int U,
+                     float slope, sg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,14 @@ SIGNATURES = {
     "sg_seg_softmax_fwd": (_c_int, [_c_p] * 3 + [_c_int] * 3 + [_c_p]),
     "sg_seg_softmax_bwd": (_c_int, [_c_p] * 4 + [_c_int] * 4 + [_c_p]),
     "sg_multilink_agg_fwd": (_c_int, [_c_p] * 6 + [_c_int] * 5 + [_c_p, _c_int, _c_p, _c_p]),
+    "sg_multilink_agg_fwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_p, _c_p] + [_c_int] * 5 +
+                                   [_c_p, _c_int, _c_p, _c_p]),
     "sg_multilink_transpose_finish": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
+    "sg_gemm_split_ws_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
+    "sg_gemm_tf32x3": (_c_int, [_c_p, _c_int, _c_p, _c_p, _c_int, _c_p, _c_p, _c_int] + [_c_int] * 5 +
+                       [ctypes.c_float, _c_int, _c_p, _c_p]),
+    "sg_split_tf32": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p]),
+    "sg_act_bwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_int, _c_int, ctypes.c_float, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),
 }
 

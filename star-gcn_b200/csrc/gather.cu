@@ -59,6 +59,20 @@ __device__ __forceinline__ void st_row(float *p, const float (&v)[VEC]) {
   else *p = v[0];
 }
 
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__device__ __forceinline__ void store_wsum(const GatherArgs &a, int seg, float wacc) {
+  const int r = seg / a.n_out_rows, i = seg - r * a.n_out_rows;
+  const long long o = (long long)i * a.wsum_ld + r;
+  if (a.wsum_lo) {
+    const float h = tf32_hi(wacc);
+    a.wsum[o] = h;
+    a.wsum_lo[o] = wacc - h;
+  } else {
+    a.wsum[o] = wacc;
+  }
+}
+
 __device__ __forceinline__ long long out_offset(const GatherArgs &a, int seg) {
   if (a.n_out_rows == a.n_seg) return (long long)seg * a.ld_out;
   int r = seg / a.n_out_rows, i = seg - r * a.n_out_rows;
@@ -160,11 +174,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
           st_row<VEC>(orow + c, r);
         }
       }
-      if (a.wsum && lane == 0 && blockIdx.z == 0) {
-        // wsum is [n_out_rows, R] with R = n_seg / n_out_rows
-        int r = d.z / a.n_out_rows, i = d.z - r * a.n_out_rows;
-        a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
-      }
+      if (a.wsum && lane == 0 && blockIdx.z == 0) store_wsum(a, d.z, wacc);
     }
   }
 }
@@ -263,11 +273,14 @@ __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs 
         const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
         acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
       }
-      reinterpret_cast<float4 *>(orow)[lane] = acc;
-      if (WSUM && lane == 0) {
-        int r = d.z / a.n_out_rows, i = d.z - r * a.n_out_rows;
-        a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
+      if (a.out_lo) {
+        const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
+        reinterpret_cast<float4 *>(orow)[lane] = hi;
+        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
+      } else {
+        reinterpret_cast<float4 *>(orow)[lane] = acc;
       }
+      if (WSUM && lane == 0) store_wsum(a, d.z, wacc);
     }
   }
 }
@@ -324,13 +337,18 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
 #pragma unroll
           for (int e = 0; e < VEC; ++e) r[e] += o[e];
         }
-        st_row<VEC>(orow + c, r);
+        if (a.out_lo) {
+          float h[VEC], l[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) { h[e] = tf32_hi(r[e]); l[e] = r[e] - h[e]; }
+          st_row<VEC>(orow + c, h);
+          st_row<VEC>(a.out_lo + (orow - a.out) + c, l);
+        } else {
+          st_row<VEC>(orow + c, r);
+        }
       }
     }
-    if (a.wsum && lane == 0 && blockIdx.z == 0) {
-      int r = d.x / a.n_out_rows, i = d.x - r * a.n_out_rows;
-      a.wsum[(long long)i * (a.n_seg / a.n_out_rows) + r] = wacc;
-    }
+    if (a.wsum && lane == 0 && blockIdx.z == 0) store_wsum(a, d.x, wacc);
   }
 }
 
@@ -434,6 +452,7 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
       default: break;
     }
   }
+  SG_REQUIRE(!a.out_lo, "pre-split (hi/lo) output needs 16-byte aligned rows of 16, 32, 64 or 128 floats");
   if (v4) return dispatch_lpr<4>(a, K, n_items_cap, n_long_cap, st);
   if (v2) return dispatch_lpr<2>(a, K, n_items_cap, n_long_cap, st);
   return dispatch_lpr<1>(a, K, n_items_cap, n_long_cap, st);

@@ -35,9 +35,14 @@ struct GatherArgs {
   int plan_chunk = 0;
   float *partial = nullptr;
   long long partial_batch_stride = 0;
-  // optional per-segment sum of weights, laid out [n_out_rows, n_seg / n_out_rows]
+  // optional per-segment sum of weights: wsum[i * wsum_ld + r] for segment r * n_out_rows + i
   float *wsum = nullptr;
+  int wsum_ld = 0;
   float *partial_wsum = nullptr;
+  // when set, results are stored pre-split for the 3xTF32 GEMM: out/wsum receive the TF32-exact
+  // high part, out_lo/wsum_lo the remainder (same offsets)
+  float *out_lo = nullptr;
+  float *wsum_lo = nullptr;
   int req = SG_REQ_WRITE;
   int mean = 0;  // divide by the segment length (seg_pool 'avg')
 };

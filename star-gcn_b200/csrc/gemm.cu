@@ -1,0 +1,502 @@
+// Relation transform on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+// The per-rating-level FullyConnected + add_n of MultiLinkGCNAggregator.hybrid_forward
+// (mxgraph/layers/aggregators.py:141-159) is, after aggregate-first reordering, ONE dense GEMM
+//     Z[n_dst, U] = [agg | wsum][n_dst, R*D + R] . [W_cat | B^T][U, R*D + R]^T
+// and its backward two more (dAgg = gZ . W_cat,  dW = gZ^T . [agg | wsum]).  fp32 parity at 1e-5
+// rules out plain TF32 (2^-11 input rounding), so every operand arrives pre-split as
+//     x = x_hi + x_lo,   x_hi = x with the low 13 mantissa bits cleared (exact in TF32)
+// and the kernel accumulates  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  into one fp32 TMEM accumulator
+// (the dropped A_lo.B_lo term is ~2^-22 relative).
+//
+// Kernel shape (one 128 x 256 output tile per CTA, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) -> STAGES-deep smem ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
+//               (M=128, N=BN, K=8) from smem descriptors; tcgen05.commit frees the stage
+//   warps 2-9   epilogue: drain each TMEM chain (tcgen05.ld 32x32b.x32) into fp32 register
+//               accumulators, then activation -> global stores
+// Operand layouts: K-major (A[M,K], B[N,K] row-major; forward and dAgg) or MN-major (A[K,M],
+// B[K,N] row-major; the weight gradient, whose reduction axis is the node axis) — the latter
+// loads [32 floats x 32 k-rows] swizzle atoms (one TMA box each) and sets the a_major/b_major
+// bits of the instruction descriptor.  Split-K partials are summed in a fixed order.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kBM = 128;        // UMMA M
+constexpr int kBK = 32;         // floats per stage row = 128 B = one swizzle span
+constexpr int kUmmaK = 8;       // tf32 MMA K
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+
+struct GemmArgs {
+  float *D;
+  long long split_stride;  // elements between split-K partial outputs
+  int ldd;
+  int M, N;
+  int kb_total;      // number of BK-wide k-blocks
+  int kb_per_split;
+  int epi;           // 0 store, 1 leaky (slope)
+  float slope;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride
+// byte offsets (all >> 4), version 1 (Blackwell), layout type 2 = SWIZZLE_128B (16-byte chunks over 8 rows);
+// layout 1 = SWIZZLE_128B_BASE32B (32-byte chunks permuted over 4 rows): the only layout the hardware
+// accepts for MN-major 32-bit operands (cutlass sm100_common.inl:92).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM kernel
+//
+// Accumulation accuracy: the tensor core adds into its fp32 TMEM accumulator with truncation
+// (measured: a 252-MMA chain at K=650 lands 3.5e-6 relative BELOW the exact magnitude, always
+// toward zero).  To stay an order of magnitude inside the 1e-5 parity bar at any K, a TMEM
+// accumulator only ever holds a chain of kChainVBlocks virtual k-blocks (24 MMAs); the epilogue
+// warps drain it (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest
+// while the MMA warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).
+// ---------------------------------------------------------------------------------------------
+constexpr int kChainVBlocks = 6;  // 2 k-blocks x 3 hi/lo products = 24 MMAs per TMEM chain
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES, bool MN_MAJOR>
+__global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                                                                      const __grid_constant__ CUtensorMap map_a_lo,
+                                                                      const __grid_constant__ CUtensorMap map_b_hi,
+                                                                      const __grid_constant__ CUtensorMap map_b_lo,
+                                                                      const GemmArgs g) {
+  static_assert(BN == 256, "two BN-column accumulators must fill the 512 TMEM columns");
+  constexpr int A_BYTES = kBM * kBK * 4;
+  constexpr int B_BYTES = BN * kBK * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
+                             ((MN_MAJOR ? 1u : 0u) << 15) | ((MN_MAJOR ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * g.kb_per_split;
+  const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+  const int n_v = (kb_end - kb_begin) * 3;  // virtual k-blocks: 3 hi/lo products per k-block
+  const int n_chains = (n_v + kChainVBlocks - 1) / kChainVBlocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int v = 0; v < n_v; ++v) {
+        const int s = v % STAGES;
+        const uint32_t ph = (v / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int kb = kb_begin + v / 3, pass = v % 3;  // pass 0: lo.hi  1: hi.lo  2: hi.hi
+        const CUtensorMap *ma = pass == 0 ? &map_a_lo : &map_a_hi;
+        const CUtensorMap *mb = pass == 1 ? &map_b_lo : &map_b_hi;
+        uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
+        if constexpr (MN_MAJOR) {  // one [32 floats x 32 k-rows] swizzle atom per load
+#pragma unroll
+          for (int a = 0; a < kBM / 32; ++a) tma_load_2d(sa + a * (kBK * 128), ma, &full_bar[s], m0 + a * 32, kb * kBK);
+#pragma unroll
+          for (int a = 0; a < BN / 32; ++a) tma_load_2d(sb + a * (kBK * 128), mb, &full_bar[s], n0 + a * 32, kb * kBK);
+        } else {
+          tma_load_2d(sa, ma, &full_bar[s], kb * kBK, m0);
+          tma_load_2d(sb, mb, &full_bar[s], kb * kBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int v = 0; v < n_v; ++v) {
+        const int s = v % STAGES;
+        const uint32_t ph = (v / STAGES) & 1;
+        const int chain = v / kChainVBlocks, vin = v - chain * kChainVBlocks;
+        const int buf = chain & 1;
+        if (vin == 0) {  // start of a chain: the epilogue warps must have drained this buffer
+          mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          uint64_t da, db;
+          if constexpr (MN_MAJOR) {  // boxes [32 floats x 32 k-rows] 4096 B apart (LBO); 4-row swizzle groups
+                                     // 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
+            da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
+            db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
+          } else {                   // rows of 128 B, 8-row groups 1024 B apart; 8 floats = 32 B per MMA
+            da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+            db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+          }
+          umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (vin | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+        if (vin == kChainVBlocks - 1 || v == n_v - 1) umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half h
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int row = m0 + q * 32 + lane;
+    const int cbase = h * (BN / 2);
+    const bool active = n0 + cbase < g.N;  // warp-uniform
+    float racc[BN / 2];
+#pragma unroll
+    for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
+    for (int chain = 0; chain < n_chains; ++chain) {
+      const int buf = chain & 1;
+      mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+      tc_fence_after();
+      if (active) {
+#pragma unroll
+        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    if (active && row < g.M) {
+      float *drow = g.D + (long long)blockIdx.z * g.split_stride + (long long)row * g.ldd;
+      const bool v4 = (g.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0 && (g.split_stride & 3) == 0;
+      const bool v2 = (g.ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 7) == 0 && (g.split_stride & 1) == 0;
+      if (g.epi == 1) {
+#pragma unroll
+        for (int j = 0; j < BN / 2; ++j) racc[j] = racc[j] > 0.f ? racc[j] : g.slope * racc[j];
+      }
+      const int col = n0 + cbase;
+      if (col + BN / 2 <= g.N && v4) {
+#pragma unroll
+        for (int j = 0; j < BN / 2; j += 4)
+          *reinterpret_cast<float4 *>(drow + col + j) = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+      } else if (v2) {
+#pragma unroll
+        for (int j = 0; j < BN / 2; j += 2) {
+          if (col + j + 1 < g.N) *reinterpret_cast<float2 *>(drow + col + j) = make_float2(racc[j], racc[j + 1]);
+          else if (col + j < g.N) drow[col + j] = racc[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 2; ++j)
+          if (col + j < g.N) drow[col + j] = racc[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// fixed-order sum of split-K partials
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(float *__restrict__ dst, int ldd, const float *__restrict__ ws,
+                                                            int M, int N, int splits) {
+  const long long total = (long long)M * N;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + t];
+    const int r = (int)(t / N), c = (int)(t - (long long)r * N);
+    dst[(long long)r * ldd + c] = acc;
+  }
+}
+
+// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly representable in TF32),
+// lo = x - hi (exact in fp32).  Optional transpose; destination padded to ld_dst with zeros.
+__global__ void __launch_bounds__(256) split_tf32_kernel(float *__restrict__ hi, float *__restrict__ lo, int ld_dst,
+                                                         const float *__restrict__ src, int rows, int cols, int ld_src,
+                                                         int transpose) {
+  const int out_rows = transpose ? cols : rows, out_cols = transpose ? rows : cols;
+  const long long total = (long long)out_rows * ld_dst;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / ld_dst), c = (int)(t - (long long)r * ld_dst);
+    float x = 0.f;
+    if (c < out_cols) x = transpose ? src[(long long)c * ld_src + r] : src[(long long)r * ld_src + c];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[t] = h;
+    lo[t] = x - h;
+  }
+}
+
+// gZ = gout * act'(Z) from the saved OUTPUT (sign(out) == sign(Z) for leaky / relu / identity),
+// written pre-split and padded: the A operand of both backward GEMMs.
+__global__ void __launch_bounds__(256) act_bwd_split_kernel(float *__restrict__ gz_hi, float *__restrict__ gz_lo, int ldz,
+                                                            const float *__restrict__ gout, const float *__restrict__ out,
+                                                            int M, int U, float slope) {
+  const long long total = (long long)M * ldz;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / ldz), c = (int)(t - (long long)r * ldz);
+    float x = 0.f;
+    if (c < U) {
+      const long long o = (long long)r * U + c;
+      const float gval = __ldg(gout + o);
+      x = __ldg(out + o) > 0.f ? gval : slope * gval;
+    }
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    gz_hi[t] = h;
+    gz_lo[t] = x - h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// K-major operand X[rows, K] (row-major, ld floats): 2-D map, box = 32 floats x box_rows
+static int make_map_kmajor(CUtensorMap *m, const float *x, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled (K-major) failed with CUresult %d", (int)r);
+  return SG_OK;
+}
+
+// MN-major operand X[K, mn] (row-major, ld floats): 2-D map (mn, K), box = 32 floats x 32 k-rows = one
+// SWIZZLE_128B_ATOM_32B box; the kernel places the atoms of a tile 4096 B apart -> smem [atom][k-row][32 floats]
+static int make_map_mnmajor(CUtensorMap *m, const float *x, int K, int mn, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)kBK};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", (int)r);
+  return SG_OK;
+}
+
+template <int BN, int STAGES, bool MN>
+static int launch_gemm(const CUtensorMap (&maps)[4], const GemmArgs &g, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * (kBM * kBK * 4 + BN * kBK * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<BN, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(g.M, kBM), (unsigned)ceil_div(g.N, BN), (unsigned)splits);
+  tf32x3_gemm_kernel<BN, STAGES, MN><<<grid, kGemmThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  SG_LAUNCHED("tf32x3_gemm_kernel");
+  return SG_OK;
+}
+
+static inline int grid_ew(long long n) {
+  long long gsz = ceil_div<long long>(n > 0 ? n : 1, 256);
+  long long cap = (long long)num_sms() * 32;
+  return (int)(gsz < cap ? gsz : cap);
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+size_t sg_gemm_split_ws_bytes(int M, int N, int splits) {
+  if (M <= 0 || N <= 0 || splits <= 1) return 0;
+  return (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+}
+
+int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int lda, const float *B_hi,
+                   const float *B_lo, int ldb, int M, int N, int K, int mn_major, int epilogue, float slope,
+                   int splits, float *split_ws, sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(M > 0 && N > 0 && K > 0, "sg_gemm_tf32x3: bad sizes M=%d N=%d K=%d", M, N, K);
+  SG_REQUIRE(D && A_hi && A_lo && B_hi && B_lo, "sg_gemm_tf32x3: null pointer");
+  SG_REQUIRE(epilogue == 0 || epilogue == 1, "sg_gemm_tf32x3: bad epilogue %d", epilogue);
+  SG_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "sg_gemm_tf32x3: operand leading dimensions must be multiples of 4 floats (TMA strides)");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) |
+                       reinterpret_cast<uintptr_t>(B_hi) | reinterpret_cast<uintptr_t>(B_lo);
+  SG_REQUIRE((al & 15) == 0, "sg_gemm_tf32x3: operands must be 16-byte aligned");
+  if (splits < 1) splits = 1;
+  SG_REQUIRE(splits == 1 || (split_ws && epilogue == 0), "sg_gemm_tf32x3: split-K needs a workspace and the plain epilogue");
+  GemmArgs g;
+  g.M = M; g.N = N; g.epi = epilogue; g.slope = slope;
+  g.kb_total = ceil_div(K, kBK);
+  g.kb_per_split = ceil_div(g.kb_total, splits);
+  splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split
+  if (splits > 1) { g.D = split_ws; g.ldd = N; g.split_stride = (long long)M * N; }
+  else { g.D = D; g.ldd = ldd; g.split_stride = 0; }
+  const int BN = 256;
+  CUtensorMap maps[4];
+  int rc;
+  if (mn_major) {
+    SG_REQUIRE(M <= lda && N <= ldb, "sg_gemm_tf32x3: MN-major leading dimensions too small");
+    if ((rc = make_map_mnmajor(&maps[0], A_hi, K, M, lda)) != SG_OK) return rc;
+    if ((rc = make_map_mnmajor(&maps[1], A_lo, K, M, lda)) != SG_OK) return rc;
+    if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
+    if ((rc = make_map_mnmajor(&maps[3], B_lo, K, N, ldb)) != SG_OK) return rc;
+    if ((rc = launch_gemm<256, 4, true>(maps, g, splits, st)) != SG_OK) return rc;
+  } else {
+    if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[1], A_lo, M, K, lda, kBM)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, BN)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[3], B_lo, N, K, ldb, BN)) != SG_OK) return rc;
+    if ((rc = launch_gemm<256, 4, false>(maps, g, splits, st)) != SG_OK) return rc;
+  }
+  if (splits > 1) {
+    splitk_reduce_kernel<<<grid_ew((long long)M * N), 256, 0, st>>>(D, ldd, split_ws, M, N, splits);
+    SG_LAUNCHED("splitk_reduce_kernel");
+  }
+  return SG_OK;
+}
+
+int sg_split_tf32(float *hi, float *lo, int ld_dst, const float *src, int rows, int cols, int ld_src, int transpose,
+                  sg_stream_t stream) {
+  SG_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols, "sg_split_tf32: bad sizes");
+  SG_REQUIRE(ld_dst >= (transpose ? rows : cols), "sg_split_tf32: ld_dst too small");
+  if (rows == 0 || cols == 0) return SG_OK;
+  SG_REQUIRE(hi && lo && src, "sg_split_tf32: null pointer");
+  const long long total = (long long)(transpose ? cols : rows) * ld_dst;
+  split_tf32_kernel<<<grid_ew(total), 256, 0, (cudaStream_t)stream>>>(hi, lo, ld_dst, src, rows, cols, ld_src, transpose);
+  SG_LAUNCHED("split_tf32_kernel");
+  return SG_OK;
+}
+
+int sg_act_bwd_split(float *gz_hi, float *gz_lo, int ldz, const float *gout, const float *out, int M, int U,
+                     float slope, sg_stream_t stream) {
+  SG_REQUIRE(M >= 0 && U >= 0 && ldz >= U, "sg_act_bwd_split: bad sizes");
+  if (M == 0 || U == 0) return SG_OK;
+  SG_REQUIRE(gz_hi && gz_lo && gout && out, "sg_act_bwd_split: null pointer");
+  act_bwd_split_kernel<<<grid_ew((long long)M * ldz), 256, 0, (cudaStream_t)stream>>>(gz_hi, gz_lo, ldz, gout, out, M, U, slope);
+  SG_LAUNCHED("act_bwd_split_kernel");
+  return SG_OK;
+}
+
+}  // extern "C"

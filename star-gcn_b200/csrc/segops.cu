@@ -385,19 +385,20 @@ int sg_seg_softmax_bwd(float *dst, const float *ograd, const float *val, const i
   return SG_OK;
 }
 
-int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x, const float *support, const int32_t *end_points,
-                         const int32_t *cat_indptr, int R, int n_dst, int n_nb, int nnz, int D, const void *plan,
-                         int plan_chunk, float *partial, sg_stream_t stream) {
+static int multilink_agg_fwd_impl(float *agg, float *agg_lo, int ld_agg, float *wsum, float *wsum_lo, int wsum_ld,
+                                  const float *x, const float *support, const int32_t *end_points,
+                                  const int32_t *cat_indptr, int R, int n_dst, int n_nb, int nnz, int D,
+                                  const void *plan, int plan_chunk, float *partial, sg_stream_t stream) {
   SG_REQUIRE(R > 0 && n_dst >= 0 && n_nb >= 0 && nnz >= 0 && D > 0, "sg_multilink_agg_fwd: bad sizes");
   SG_REQUIRE((long long)R * n_dst < (1LL << 31), "sg_multilink_agg_fwd: R*n_dst overflows int32");
   if (n_dst == 0) return SG_OK;
   SG_REQUIRE(agg && cat_indptr && (nnz == 0 || (x && support && end_points)), "sg_multilink_agg_fwd: null pointer");
   const int n_seg = R * n_dst;
   GatherArgs a;
-  a.out = agg; a.ld_out = R * D; a.n_out_rows = n_dst;
+  a.out = agg; a.out_lo = agg_lo; a.ld_out = ld_agg; a.n_out_rows = n_dst;
   a.src = x; a.ld_src = D;
   a.w = support; a.idx = end_points; a.indptr = cat_indptr; a.F = D; a.req = SG_REQ_WRITE;
-  a.wsum = wsum;
+  a.wsum = wsum; a.wsum_lo = wsum_lo; a.wsum_ld = wsum_ld;
   a.plan_chunk = plan_chunk;
   if (plan) {
     // partial scratch: rows of D floats followed by one weight-sum per row
@@ -406,6 +407,22 @@ int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x, const float *s
     a.partial_wsum = (wsum && partial) ? partial + rows * (size_t)D : nullptr;
   }
   return run_gather(a, 1, n_seg, nnz, plan, (cudaStream_t)stream);
+}
+
+int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x, const float *support, const int32_t *end_points,
+                         const int32_t *cat_indptr, int R, int n_dst, int n_nb, int nnz, int D, const void *plan,
+                         int plan_chunk, float *partial, sg_stream_t stream) {
+  return multilink_agg_fwd_impl(agg, nullptr, R * D, wsum, nullptr, R, x, support, end_points, cat_indptr, R, n_dst,
+                                n_nb, nnz, D, plan, plan_chunk, partial, stream);
+}
+
+int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const float *x, const float *support,
+                               const int32_t *end_points, const int32_t *cat_indptr, int R, int n_dst, int n_nb,
+                               int nnz, int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream) {
+  SG_REQUIRE(agg_lo, "sg_multilink_agg_fwd_split: null pointer");
+  SG_REQUIRE(ld_agg >= R * D + R && (ld_agg & 3) == 0, "sg_multilink_agg_fwd_split: ld_agg must be a multiple of 4 and >= R*D + R");
+  return multilink_agg_fwd_impl(agg_hi, agg_lo, ld_agg, agg_hi + (size_t)R * D, agg_lo + (size_t)R * D, ld_agg, x, support,
+                                end_points, cat_indptr, R, n_dst, n_nb, nnz, D, plan, plan_chunk, partial, stream);
 }
 
 int sg_multilink_agg_bwd(float *gx, const float *gagg, const float *t_w, const int32_t *t_src,
