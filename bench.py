@@ -312,13 +312,25 @@ def run_gpu_arm(args, rank, world, local_rank):
     except Exception:
         pass
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    detail, tot_bytes, tot_ms = {}, 0.0, 0.0
+    detail, gemm, tot_bytes, tot_ms = {}, {}, 0.0, 0.0
     for tag, a, b, csr in prof:
-        fwd = tag == "agg_fwd"
         key = f"{tag}:{'user' if csr is sides['user']['csr'] else 'item'}"
+        if tag.startswith("gemm"):
+            Kx = R * D + R
+            m, n, k = {"gemm_fwd": (csr.n_dst, U, Kx), "gemm_dagg": (csr.n_dst, R * D, U), "gemm_dw": (U, Kx, csr.n_dst)}[tag]
+            d = gemm.setdefault(key, dict(ms=0.0, n=0, flops=2.0 * m * n * k))
+            d["ms"] += a.elapsed_time(b); d["n"] += 1
+            continue
+        fwd = tag == "agg_fwd"
         by = algorithmic_bytes(csr.nnz, csr.n_seg, csr.n_nb, D, fwd)
         d = detail.setdefault(key, dict(ms=0.0, n=0, bytes=by, edges=csr.nnz))
         d["ms"] += a.elapsed_time(b); d["n"] += 1
+    gemm_ms, gemm_flops = 0.0, 0.0
+    for key, d in gemm.items():
+        d["ms"] /= max(d["n"], 1)
+        d["tflops_fp32_equiv"] = d["flops"] / (d["ms"] * 1e-3) / 1e12     # algorithmic 2MNK
+        d["tflops_tf32_issued"] = 3 * d["tflops_fp32_equiv"]                # three TF32 products per fp32 product
+        gemm_ms += d["ms"]; gemm_flops += d["flops"]
     for key, d in detail.items():
         d["ms"] /= max(d["n"], 1)
         d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
@@ -334,6 +346,13 @@ def run_gpu_arm(args, rank, world, local_rank):
                     peak=peak_gbs, peak_source=peak_src, unit="GB/s", frac=(tot_bytes / (tot_ms * 1e-3) / 1e9 / peak_gbs) if tot_ms else None,
                     traffic=traffic, share_of_step=tot_ms / ms_per_step if ms_per_step else None,
                     per_launch={k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in detail.items()})
+    transform = None
+    if gemm:
+        transform = dict(kernel="tf32x3_gemm_kernel (tcgen05 3xTF32, 6 launches/step)", bound="tensor", ms_per_step=gemm_ms,
+                         share_of_step=gemm_ms / ms_per_step if ms_per_step else None,
+                         tflops_fp32_equiv=gemm_flops / (gemm_ms * 1e-3) / 1e12, tflops_tf32_issued=3 * gemm_flops / (gemm_ms * 1e-3) / 1e12,
+                         peak_tf32_nominal=1100.0, unit="TFLOP/s",
+                         per_launch={k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in gemm.items()})
 
     # ---- end to end through the public layer API with HOST buffers (H2D + D2H inside) ----
     e2e = None
@@ -352,6 +371,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                                   (sum(algorithmic_bytes(s['csr'].nnz, s['csr'].n_seg, s['csr'].n_nb, 0, True) for s in sides.values()) * 2
                                    + sum(s['n_dst'] * (R * D + U) * 4 * 3 for s in sides.values())) / 1e6)),
                   clocks=clocks, gpu_launches=int(launches), roofline=roofline)
+    if transform is not None:
+        result["transform_gemm"] = transform
     if e2e is not None:
         result["e2e"] = e2e
     return result, wl

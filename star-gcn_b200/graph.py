@@ -196,6 +196,140 @@ class _MultiLinkAgg(torch.autograd.Function):
         return gx, None
 
 
+def _split_tf32(src, ld_dst, transpose=False):
+    """(hi, lo) of a 2-D fp32 tensor, padded to ld_dst columns (sg_split_tf32)."""
+    lib = _lib.load()
+    rows, cols = src.shape
+    if src.stride(1) != 1:
+        src = src.contiguous()
+    out_rows = cols if transpose else rows
+    hi = torch.empty((out_rows, ld_dst), dtype=torch.float32, device=src.device)
+    lo = torch.empty_like(hi)
+    check(lib.sg_split_tf32(_p(hi), _p(lo), ld_dst, _p(src), rows, cols, src.stride(0), int(transpose), _stream()),
+          "sg_split_tf32")
+    return hi, lo
+
+
+def _gemm_tf32x3(D, a_hi, a_lo, b_hi, b_lo, M, N, K, mn_major=False, epilogue=0, slope=0.0, splits=1):
+    lib = _lib.load()
+    ws = None
+    if splits > 1:
+        ws = torch.empty(int(lib.sg_gemm_split_ws_bytes(M, N, splits)) // 4, dtype=torch.float32, device=D.device)
+    check(lib.sg_gemm_tf32x3(_p(D), D.stride(0), _p(a_hi), _p(a_lo), a_hi.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0),
+                             M, N, K, int(mn_major), int(epilogue), ctypes.c_float(slope), int(splits), _p(ws),
+                             _stream()), "sg_gemm_tf32x3")
+    return D
+
+
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+FUSED_DIMS = (16, 32, 64, 128)
+
+
+class _FusedAggTransform(torch.autograd.Function):
+    """out = act([agg | wsum] . w_ext^T): the whole MultiLinkGCNAggregator (accum='sum') in one gather
+    launch + one tcgen05 GEMM; backward = activation gradient (pre-split), two GEMMs and the transposed
+    gather.  w_ext [U, R*D + R] = [W_0 | ... | W_{R-1} | b_0 ... b_{R-1}]."""
+
+    @staticmethod
+    def forward(ctx, x, w_ext, csr, slope):
+        lib = _lib.load()
+        n_nb, D = x.shape
+        R, n_dst = csr.R, csr.n_dst
+        U, Kx = w_ext.shape
+        assert Kx == R * D + R
+        ld = (Kx + 31) // 32 * 32
+        dev = x.device
+        agg_hi = torch.empty((max(n_dst, 1), ld), dtype=torch.float32, device=dev)
+        agg_lo = torch.empty_like(agg_hi)
+        sched = csr.schedule()
+        if sched is not None:
+            part = sched.partial(1, D, extra_per_row=1)
+            plan, chunk, pp = _p(sched.buf), sched.chunk, _p(part)
+        else:
+            plan, chunk, pp = ctypes.c_void_p(0), 0, ctypes.c_void_p(0)
+        e0 = _prof_begin()
+        check(lib.sg_multilink_agg_fwd_split(_p(agg_hi), _p(agg_lo), ld, _p(x), _p(csr.support), _p(csr.end_points),
+                                             _p(csr.cat_indptr), R, n_dst, n_nb, csr.nnz, D, plan, chunk, pp,
+                                             _stream()), "sg_multilink_agg_fwd_split")
+        _prof_end("agg_fwd", e0, csr)
+        w_hi, w_lo = _split_tf32(w_ext, ld)
+        out = torch.empty((n_dst, U), dtype=torch.float32, device=dev)
+        if n_dst > 0:
+            e0 = _prof_begin()
+            _gemm_tf32x3(out, agg_hi, agg_lo, w_hi, w_lo, n_dst, U, Kx, epilogue=1, slope=slope)
+            _prof_end("gemm_fwd", e0, csr)
+        ctx.csr, ctx.slope, ctx.dims = csr, slope, (n_nb, D, R, n_dst, U, Kx, ld)
+        ctx.save_for_backward(agg_hi, agg_lo, out, w_ext)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        agg_hi, agg_lo, out, w_ext = ctx.saved_tensors
+        csr, slope = ctx.csr, ctx.slope
+        n_nb, D, R, n_dst, U, Kx, ld = ctx.dims
+        dev = gout.device
+        gout = gout.contiguous()
+        ldz = (U + 3) // 4 * 4
+        gz_hi = torch.empty((max(n_dst, 1), ldz), dtype=torch.float32, device=dev)
+        gz_lo = torch.empty_like(gz_hi)
+        check(lib.sg_act_bwd_split(_p(gz_hi), _p(gz_lo), ldz, _p(gout), _p(out), n_dst, U, ctypes.c_float(slope),
+                                   _stream()), "sg_act_bwd_split")
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((n_nb, D), dtype=torch.float32, device=dev)
+            if n_dst > 0:
+                wt_hi, wt_lo = _split_tf32(w_ext[:, :R * D], ldz, transpose=True)       # [R*D, ldz]
+                gagg = torch.empty((n_dst, R * D), dtype=torch.float32, device=dev)
+                e0 = _prof_begin()
+                _gemm_tf32x3(gagg, gz_hi, gz_lo, wt_hi, wt_lo, n_dst, R * D, U)
+                _prof_end("gemm_dagg", e0, csr)
+            else:
+                gagg = torch.zeros((0, R * D), dtype=torch.float32, device=dev)
+            t_indptr, t_src, t_w = csr.transposed()
+            sched = csr.t_schedule()
+            if sched is not None:
+                part = sched.partial(1, D)
+                plan, chunk, pp = _p(sched.buf), sched.chunk, _p(part)
+            else:
+                plan, chunk, pp = ctypes.c_void_p(0), 0, ctypes.c_void_p(0)
+            e0 = _prof_begin()
+            check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, n_dst, n_nb, csr.nnz,
+                                           D, 1, plan, chunk, pp, _stream()), "sg_multilink_agg_bwd")
+            _prof_end("agg_bwd", e0, csr)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros((U, Kx), dtype=torch.float32, device=dev) if n_dst == 0 else \
+                torch.empty((U, Kx), dtype=torch.float32, device=dev)
+            if n_dst > 0:
+                tiles = ((U + 127) // 128) * ((Kx + 255) // 256)
+                kb = (n_dst + 31) // 32
+                splits = max(1, min(_sm_count(dev) // tiles, kb // 4))
+                e0 = _prof_begin()
+                _gemm_tf32x3(gw, gz_hi, gz_lo, agg_hi, agg_lo, U, Kx, n_dst, mn_major=True, splits=splits)
+                _prof_end("gemm_dw", e0, csr)
+        return gx, gw, None, None
+
+
+def fused_agg_transform(x, w_ext, csr, slope):
+    """act([agg | wsum] . w_ext^T) with act = leaky(slope) (slope 1.0 = identity, 0.0 = ReLU)."""
+    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
+        raise TypeError("x must be a 2-D float32 CUDA tensor")
+    if x.shape[0] != csr.n_nb:
+        raise ValueError(f"x has {x.shape[0]} rows but the plan indexes {csr.n_nb} neighbour rows")
+    if x.shape[1] not in FUSED_DIMS:
+        raise ValueError(f"the fused path needs D in {FUSED_DIMS}")
+    return _FusedAggTransform.apply(x.contiguous(), w_ext, csr, float(slope))
+
+
 def multilink_aggregate(x, csr):
     """Fused all-relations neighbour aggregation; returns (agg [n_dst, R*D], wsum [n_dst, R])."""
     if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:

@@ -19,8 +19,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import seg_op
-from ..graph import MultiLinkCSR, multilink_aggregate
-from .common import get_activation, xavier_in_uniform_
+from ..graph import FUSED_DIMS, MultiLinkCSR, fused_agg_transform, multilink_aggregate
+from .common import activation_code, get_activation, xavier_in_uniform_
 
 
 class BaseAggregator(nn.Module):
@@ -52,6 +52,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
             assert units % num_links == 0, "units should be divisible by the num_links "
             self._units = self._units // num_links
         self.reference_order = reference_order
+        self.tensor_cores = True   # False: fp32 cuBLAS transform after the fused gather (A/B comparison)
         self.dropout = nn.Dropout(dropout_rate)
         # parameters are named weight{i} / bias{i} as in the reference (aggregators.py:86-97)
         for i in range(num_links):
@@ -124,8 +125,13 @@ class MultiLinkGCNAggregator(BaseAggregator):
         csr = self._plan(neighbor_data.shape[0], end_points_l, indptr_l, support_l)
         if csr.R != self._num_links:
             raise ValueError(f"plan has {csr.R} links, aggregator was built for {self._num_links}")
-        agg, wsum = multilink_aggregate(neighbor_data, csr)           # (n_dst, R*D), (n_dst, R)
         D = neighbor_data.shape[1]
+        code = activation_code(self._act)
+        if (self._accum == "sum" or self._num_links == 1) and D in FUSED_DIMS and code is not None and self.tensor_cores:
+            # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
+            w_ext = torch.cat(ws + [torch.stack(bs, dim=1)], dim=1)   # (U, R*D + R)
+            return fused_agg_transform(neighbor_data, w_ext, csr, {0: 1.0, 1: 0.1, 2: 0.0}[code])
+        agg, wsum = multilink_aggregate(neighbor_data, csr)           # (n_dst, R*D), (n_dst, R)
         if self._accum == "sum" or self._num_links == 1:
             w_cat = torch.cat(ws, dim=1)                              # (U, R*D)
             b_mat = torch.stack(bs, dim=0)                            # (R, U)
