@@ -187,7 +187,8 @@ int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, 
 size_t sg_gemm_split_ws_bytes(int M, int N, int splits);
 int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int lda, const float *B_hi,
                    const float *B_lo, int ldb, int M, int N, int K, int mn_major, int epilogue, float slope,
-                   int splits, float *split_ws, sg_stream_t stream);
+                   const float *bias /*N or NULL, added before the activation*/, int splits, float *split_ws,
+                   sg_stream_t stream);
 /* hi = src with the 13 low mantissa bits cleared, lo = src - hi; optional transpose; the
  * destination has ld_dst >= columns and its padding is zero-filled. */
 int sg_split_tf32(float *hi, float *lo, int ld_dst, const float *src, int rows, int cols, int ld_src,
@@ -197,6 +198,34 @@ int sg_split_tf32(float *hi, float *lo, int ld_dst, const float *src, int rows, 
  * (replaces MXNet's LeakyReLU backward, mxgraph/layers/common.py:46-47). */
 int sg_act_bwd_split(float *gz_hi, float *gz_lo, int ldz, const float *gout, const float *out, int M, int U,
                      float slope, sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * D1-D4  masked-embedding reconstruction decoder and rating head (experiments/STAR-GCN.py)
+ * ---------------------------------------------------------------------------------------- */
+/* D1  Net.get_embed (STAR-GCN.py:264-300): id' = noise ? noise[ids[i]] : ids[i];
+ * out[i,:] = id' == -1 ? 0 : table[id',:];  eff_ids[i] = id' (kept for the backward scatter).
+ * Replaces take + not_equal + mul + Embedding + mul (5 MXNet launches). */
+int sg_masked_embed_fwd(float *out /*n,D*/, int32_t *eff_ids /*n*/, const float *table /*n_table,D*/,
+                        const int32_t *ids /*n*/, const int32_t *noise /*n_table or NULL*/, int n, int n_table,
+                        int D, sg_stream_t stream);
+/* D3  loss = scale * sum_i sum_d (a[i,d] - b[i,d])^2 — mx.nd.mean(mx.nd.sum(mx.nd.square(gt - pred), -1))
+ * with scale = 1/n (STAR-GCN.py:625) and gluon L2Loss(...).mean() with D = 1, scale = 0.5/n (:611-616).
+ * Two-stage fixed-order reduction (bit-identical reruns); ws needs sg_reduce_ws_bytes() bytes. */
+size_t sg_reduce_ws_bytes(void);
+int sg_sq_err_fwd(float *loss /*1*/, const float *a, const float *b, long long n_elem, float scale, void *ws,
+                  sg_stream_t stream);
+/* ga = 2 * scale * gloss[0] * (a - b),  gb = -ga  (either may be NULL) */
+int sg_sq_err_bwd(float *ga, float *gb, const float *a, const float *b, const float *gloss /*1, device*/,
+                  long long n_elem, float scale, sg_stream_t stream);
+/* D4  InnerProductLayer without mid map (mxgraph/layers/layers.py:217-222): out[i] = <a[i,:], b[i,:]> */
+int sg_rowdot_fwd(float *out /*n*/, const float *a, const float *b, int n, int D, sg_stream_t stream);
+int sg_rowdot_bwd(float *ga, float *gb, const float *gout /*n*/, const float *a, const float *b, int n, int D,
+                  sg_stream_t stream);
+/* Bias gradient of a Dense layer: out[c] = sum_r (x_hi[r,c] + x_lo[r,c]) over a pre-split operand
+ * (x_lo may be NULL); fixed-order two-stage reduction; ws needs sg_colsum_ws_bytes(N) bytes. */
+size_t sg_colsum_ws_bytes(int N);
+int sg_colsum(float *out /*N*/, const float *x_hi, const float *x_lo, int M, int N, int ld, void *ws,
+              sg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,15 @@ SIGNATURES = {
     "sg_multilink_transpose_finish": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
     "sg_gemm_split_ws_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "sg_gemm_tf32x3": (_c_int, [_c_p, _c_int, _c_p, _c_p, _c_int, _c_p, _c_p, _c_int] + [_c_int] * 5 +
-                       [ctypes.c_float, _c_int, _c_p, _c_p]),
+                       [ctypes.c_float, _c_p, _c_int, _c_p, _c_p]),
+    "sg_masked_embed_fwd": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
+    "sg_reduce_ws_bytes": (_c_sz, []),
+    "sg_sq_err_fwd": (_c_int, [_c_p, _c_p, _c_p, ctypes.c_longlong, ctypes.c_float, _c_p, _c_p]),
+    "sg_sq_err_bwd": (_c_int, [_c_p] * 5 + [ctypes.c_longlong, ctypes.c_float, _c_p]),
+    "sg_rowdot_fwd": (_c_int, [_c_p] * 3 + [_c_int] * 2 + [_c_p]),
+    "sg_rowdot_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 2 + [_c_p]),
+    "sg_colsum_ws_bytes": (_c_sz, [_c_int]),
+    "sg_colsum": (_c_int, [_c_p] * 3 + [_c_int] * 3 + [_c_p, _c_p]),
     "sg_split_tf32": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p]),
     "sg_act_bwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_int, _c_int, ctypes.c_float, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),

@@ -39,6 +39,7 @@ struct GemmArgs {
   int kb_per_split;
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
+  const float *bias; // optional [N], added before the activation
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -273,11 +274,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
       float *drow = g.D + (long long)blockIdx.z * g.split_stride + (long long)row * g.ldd;
       const bool v4 = (g.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0 && (g.split_stride & 3) == 0;
       const bool v2 = (g.ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 7) == 0 && (g.split_stride & 1) == 0;
+      const int col = n0 + cbase;
+      if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < BN / 2; ++j)
+          if (col + j < g.N) racc[j] += __ldg(g.bias + col + j);
+      }
       if (g.epi == 1) {
 #pragma unroll
         for (int j = 0; j < BN / 2; ++j) racc[j] = racc[j] > 0.f ? racc[j] : g.slope * racc[j];
       }
-      const int col = n0 + cbase;
       if (col + BN / 2 <= g.N && v4) {
 #pragma unroll
         for (int j = 0; j < BN / 2; j += 4)
@@ -435,7 +441,7 @@ size_t sg_gemm_split_ws_bytes(int M, int N, int splits) {
 
 int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int lda, const float *B_hi,
                    const float *B_lo, int ldb, int M, int N, int K, int mn_major, int epilogue, float slope,
-                   int splits, float *split_ws, sg_stream_t stream) {
+                   const float *bias, int splits, float *split_ws, sg_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SG_REQUIRE(M > 0 && N > 0 && K > 0, "sg_gemm_tf32x3: bad sizes M=%d N=%d K=%d", M, N, K);
   SG_REQUIRE(D && A_hi && A_lo && B_hi && B_lo, "sg_gemm_tf32x3: null pointer");
@@ -445,9 +451,9 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
                        reinterpret_cast<uintptr_t>(B_hi) | reinterpret_cast<uintptr_t>(B_lo);
   SG_REQUIRE((al & 15) == 0, "sg_gemm_tf32x3: operands must be 16-byte aligned");
   if (splits < 1) splits = 1;
-  SG_REQUIRE(splits == 1 || (split_ws && epilogue == 0), "sg_gemm_tf32x3: split-K needs a workspace and the plain epilogue");
+  SG_REQUIRE(splits == 1 || (split_ws && epilogue == 0 && !bias), "sg_gemm_tf32x3: split-K needs a workspace and the plain epilogue");
   GemmArgs g;
-  g.M = M; g.N = N; g.epi = epilogue; g.slope = slope;
+  g.M = M; g.N = N; g.epi = epilogue; g.slope = slope; g.bias = bias;
   g.kb_total = ceil_div(K, kBK);
   g.kb_per_split = ceil_div(g.kb_total, splits);
   splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split

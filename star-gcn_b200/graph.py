@@ -210,13 +210,13 @@ def _split_tf32(src, ld_dst, transpose=False):
     return hi, lo
 
 
-def _gemm_tf32x3(D, a_hi, a_lo, b_hi, b_lo, M, N, K, mn_major=False, epilogue=0, slope=0.0, splits=1):
+def _gemm_tf32x3(D, a_hi, a_lo, b_hi, b_lo, M, N, K, mn_major=False, epilogue=0, slope=0.0, splits=1, bias=None):
     lib = _lib.load()
     ws = None
     if splits > 1:
         ws = torch.empty(int(lib.sg_gemm_split_ws_bytes(M, N, splits)) // 4, dtype=torch.float32, device=D.device)
     check(lib.sg_gemm_tf32x3(_p(D), D.stride(0), _p(a_hi), _p(a_lo), a_hi.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0),
-                             M, N, K, int(mn_major), int(epilogue), ctypes.c_float(slope), int(splits), _p(ws),
+                             M, N, K, int(mn_major), int(epilogue), ctypes.c_float(slope), _p(bias), int(splits), _p(ws),
                              _stream()), "sg_gemm_tf32x3")
     return D
 

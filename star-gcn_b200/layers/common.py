@@ -94,7 +94,11 @@ class Dense(nn.Module):
         if self._use_bias:
             self.bias = nn.Parameter(torch.zeros(self._units, dtype=torch.float32, device=device))
 
-    def forward(self, x):
+    def forward(self, x, act=None):
+        """x W^T + b on the tcgen05 GEMM; ``act`` in {None, 'leaky', 'relu'} rides in its epilogue."""
+        from ..decoder import fused_dense
         if isinstance(self.weight, nn.UninitializedParameter):
             self._materialize(x.shape[-1], x.device)
-        return F.linear(x, self.weight, self.bias)
+        lead = x.shape[:-1]
+        y = fused_dense(x.reshape(-1, x.shape[-1]), self.weight, self.bias, act)
+        return y.reshape(*lead, self._units)

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from ..graph import MultiLinkCSR
 from .aggregators import GCNAggregator, MultiLinkGCNAggregator
-from .common import Dense, get_activation
+from .common import Dense, activation_code, get_activation
 
 
 class LayerDictionary(nn.Module):
@@ -116,8 +116,10 @@ class HeterGCNLayer(nn.Module):
             out = torch.stack(out_l, dim=0).sum(dim=0)
         else:
             raise NotImplementedError
-        out = self._out_fcs[key](out)
-        return self._out_act(out)
+        code = activation_code(self._out_act)
+        if code is not None:  # activation rides in the GEMM epilogue
+            return self._out_fcs[key](out, act={0: None, 1: "leaky", 2: "relu"}[code])
+        return self._out_act(self._out_fcs[key](out))
 
     def forward(self, base_feas, neighbor_data):
         out = {}
@@ -138,7 +140,8 @@ class InnerProductLayer(nn.Module):
         if self._mid_units is not None:
             data1 = self._mid_map(data1)
             data2 = self._mid_map(data2)
-        return torch.sum(data1 * data2, dim=1, keepdim=True)
+        from ..decoder import inner_product
+        return inner_product(data1, data2)
 
 
 def _take_rows(x, idx):

@@ -43,7 +43,7 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, mn_major=False, epilogue=0, slope=0.0,
     if splits > 1:
         ws = torch.empty(lib.sg_gemm_split_ws_bytes(M, N, splits) // 4, dtype=torch.float32, device=a_hi.device)
     _lib.check(lib.sg_gemm_tf32x3(_p(D), ldd, _p(a_hi), _p(a_lo), a_hi.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0),
-                                  M, N, K, int(mn_major), epilogue, ctypes.c_float(slope), splits,
+                                  M, N, K, int(mn_major), epilogue, ctypes.c_float(slope), None, splits,
                                   _p(ws) if ws is not None else None, _stream()), "sg_gemm_tf32x3")
     return D
 
