@@ -46,33 +46,45 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def load_workload(name, seed=1000):
-    """Synthetic graph of the named shape; cached under /tmp because generation takes ~25 s."""
+def load_base(name, seed=1000):
+    """Synthetic base graph of the named shape (synth.make_bipartite); cached under /tmp (generation ~25 s)."""
     from stargcn_b200 import synth
-    cache = f"/tmp/stargcn_b200_{name}_{seed}.npz"
+    n_user, n_item, n_edges, n_levels, D = synth.SHAPES[name]
+    cache = f"/tmp/stargcn_b200_base_{name}_{seed}.npz"
     if os.path.exists(cache):
         try:
             z = np.load(cache)
-            d = dict(R=int(z["R"]), D=int(z["D"]), n_user=int(z["n_user"]), n_item=int(z["n_item"]), nnz=int(z["nnz"]),
-                     x_user=z["x_user"], x_item=z["x_item"])
-            for side in ("user", "item"):
-                d[side] = tuple([z[f"{side}_{k}_{r}"] for r in range(d["R"])] for k in ("ep", "ptr", "sup"))
-            return d
+            g = dict(n_user=int(z["n_user"]), n_item=int(z["n_item"]), nnz=int(z["nnz"]), levels=z["levels"], D=D, R=n_levels)
+            for d in ("u2i", "i2u"):
+                g[d] = {k: z[f"{d}_{k}"] for k in ("indptr", "cols", "vals", "support", "rows")}
+            return g
         except Exception:
             pass
-    d = synth.make_layer_inputs(name, seed)
+    g = synth.make_bipartite(n_user, n_item, n_edges, n_levels, seed)
+    g["D"], g["R"] = D, n_levels
     try:
-        flat = dict(R=d["R"], D=d["D"], n_user=d["n_user"], n_item=d["n_item"], nnz=d["nnz"], x_user=d["x_user"],
-                    x_item=d["x_item"])
-        for side in ("user", "item"):
-            for k, lst in zip(("ep", "ptr", "sup"), d[side][:3]):
-                for r, a in enumerate(lst):
-                    flat[f"{side}_{k}_{r}"] = a
+        flat = dict(n_user=g["n_user"], n_item=g["n_item"], nnz=g["nnz"], levels=g["levels"])
+        for d in ("u2i", "i2u"):
+            for k, v in g[d].items():
+                flat[f"{d}_{k}"] = v
         np.savez(cache + ".tmp.npz", **flat)
         os.replace(cache + ".tmp.npz", cache)
     except Exception:
         pass
-    d["user"], d["item"] = tuple(d["user"][:3]), tuple(d["item"][:3])
+    return g
+
+
+def load_workload(name, seed=1000):
+    """Single-device layer inputs: per-level CSR lists of both directions + features."""
+    from stargcn_b200 import synth
+    g = load_base(name, seed)
+    rng = np.random.default_rng(seed + 1)
+    d = dict(R=g["R"], D=g["D"], n_user=g["n_user"], n_item=g["n_item"], nnz=g["nnz"], base=g)
+    d["x_user"] = rng.standard_normal((g["n_user"], g["D"]), dtype=np.float32)
+    d["x_item"] = rng.standard_normal((g["n_item"], g["D"]), dtype=np.float32)
+    for side, key in (("user", "u2i"), ("item", "i2u")):
+        c = g[key]
+        d[side] = tuple(synth.split_by_level(c["indptr"], c["cols"], c["vals"], c["support"], g["levels"])[:3])
     return d
 
 
@@ -246,7 +258,14 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    wl = load_workload(args.workload)
+    if world > 1:
+        if rank == 0:
+            load_base(args.workload)      # generate + cache once; the other ranks read the cache
+        dist.barrier()
+        base = load_base(args.workload)
+        wl = dict(R=base["R"], D=base["D"], n_user=base["n_user"], n_item=base["n_item"], nnz=base["nnz"], base=base)
+    else:
+        wl = load_workload(args.workload)
     R, D, U = wl["R"], wl["D"], AGG_UNITS
     ws, bs = make_params(R, D, U)
 
@@ -257,26 +276,52 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- device-resident state: inputs live in HBM before the timed region starts ----
     sides = {}
-    for side, x_nb, n_dst in (("user", wl["x_item"], wl["n_user"]), ("item", wl["x_user"], wl["n_item"])):
-        csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
+    if world == 1:
+        for side, x_nb, n_dst in (("user", wl["x_item"], wl["n_user"]), ("item", wl["x_user"], wl["n_item"])):
+            csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
+            sides[side] = dict(csr=csr, x_np=x_nb, n_dst=n_dst, plan=None)
+    else:
+        # node-partitioned path: this rank owns an ML-10M-shaped slice of a world-times larger graph and
+        # fetches the neighbour rows it does not own with one all-to-all per layer direction
+        from stargcn_b200 import dist as sgd, synth
+        part = sgd.partitioned_layer_inputs(wl["base"], rank, world)
+        rng = np.random.default_rng(2000 + rank)
+        for side, nb_ranges, n_dst in (("user", part["item_ranges"], wl["n_user"]), ("item", part["user_ranges"], wl["n_item"])):
+            indptr, cols, vals, sup = part[side]
+            plan = sgd.HaloPlan(cols, nb_ranges, rank, world, index_device=dev).to(dev)
+            lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, wl["base"]["levels"])[:3]
+            csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev).prepare(backward=True)
+            x_np = rng.standard_normal((plan.n_local, D), dtype=np.float32)
+            sides[side] = dict(csr=csr, x_np=x_np, n_dst=n_dst, plan=plan)
+    for side, s_ in sides.items():
         agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", dropout_rate=0.0, ordinal_sharing=False,
                                      accum="sum", in_units=D).to(dev)
         with torch.no_grad():
             for i in range(R):
                 getattr(agg, f"weight{i}").copy_(torch.from_numpy(ws[i]))
                 getattr(agg, f"bias{i}").copy_(torch.from_numpy(bs[i]))
-        x = torch.from_numpy(x_nb).to(dev).requires_grad_(True)
-        gout = torch.randn((n_dst, U), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
-        sides[side] = dict(csr=csr, agg=agg, x=x, gout=gout, n_dst=n_dst)
+        s_["agg"] = agg
+        s_["x"] = torch.from_numpy(s_["x_np"]).to(dev).requires_grad_(True)
+        s_["gout"] = torch.randn((s_["n_dst"], U), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
     edges_per_step = sum(s["csr"].nnz for s in sides.values())
+    all_params = [p for s_ in sides.values() for p in s_["agg"].parameters()]
+    total_edges = edges_per_step
+    halo_rows = sum(s_["plan"].n_halo for s_ in sides.values() if s_["plan"] is not None)
+    if world > 1:
+        t = torch.tensor([float(edges_per_step)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        total_edges = int(t.item())
 
     def step():
         for s in sides.values():
             s["x"].grad = None
             for p in s["agg"].parameters():
                 p.grad = None
-            out = s["agg"](s["x"], s["csr"])
+            xin = s["x"] if s["plan"] is None else sgd.halo_exchange(s["x"], s["plan"])
+            out = s["agg"](xin, s["csr"])
             out.backward(s["gout"])
+        if world > 1:
+            sgd.allreduce_grads(all_params)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -303,7 +348,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = edges_per_step * world / (ms_per_step * 1e-3)
+    value = total_edges / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (gather_rows_kernel), from events on its own stream ----
     peaks = {}
@@ -357,7 +402,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     # ---- end to end through the public layer API with HOST buffers (H2D + D2H inside) ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, wl, sides, dev, world, barrier)
+        e2e = run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params)
 
     result = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                   ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -366,7 +411,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                                        f"{wl['nnz']} edges/direction, R={R} levels, D={D}, agg units={U}; one HeterGCN layer, both "
                                        f"directions, fwd+bwd; full neighbourhood",
                               edges_per_step_per_gpu=edges_per_step,
-                              parallelism="single GPU" if world == 1 else f"{world} independent replicas (no exchange)",
+                              parallelism="single GPU" if world == 1 else
+                              f"node-partitioned over {world} GPUs (each rank owns an ML-10M-shaped slice of a {world}x larger graph); "
+                              f"per layer direction one NCCL all-to-all of halo rows fwd + its transpose bwd, all-reduce of weight grads; "
+                              f"rank 0 halo = {halo_rows} rows x {D * 4} B per step-direction pair",
+                              total_edges_per_step=total_edges,
                               l2="inputs exceed L2: ~%.0f MB of CSR/feature/intermediate traffic per step vs 126 MB L2; no flush" % (
                                   (sum(algorithmic_bytes(s['csr'].nnz, s['csr'].n_seg, s['csr'].n_nb, 0, True) for s in sides.values()) * 2
                                    + sum(s['n_dst'] * (R * D + U) * 4 * 3 for s in sides.values())) / 1e6)),
@@ -378,20 +427,23 @@ def run_gpu_arm(args, rank, world, local_rank):
     return result, wl
 
 
-def run_e2e(args, wl, sides, dev, world, barrier):
+def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
     """Same step through the public API starting from PINNED HOST buffers: per step the CSR lists,
     features and upstream gradient are copied host->device, the device plan (concatenated CSR, stable
     transpose, schedules) is rebuilt — the reference re-uploads and re-sorts per call too
-    (layers.py:366-377, seg_op.cu:882-926) — forward + backward run, and a scalar read-back ends it."""
+    (layers.py:366-377, seg_op.cu:882-926) — forward + backward run (with the halo exchange and the
+    gradient all-reduce when partitioned), and a scalar read-back ends it."""
     import torch
     from stargcn_b200.graph import MultiLinkCSR
+    if world > 1:
+        from stargcn_b200 import dist as sgd
     R, D = wl["R"], wl["D"]
     host = {}
     h2d = 0
-    for side, x_nb in (("user", wl["x_item"]), ("item", wl["x_user"])):
+    for side in ("user", "item"):
         csr = sides[side]["csr"]
         host[side] = dict(ep=csr.end_points.cpu().pin_memory(), sup=csr.support.cpu().pin_memory(),
-                          ptr=csr.cat_indptr.cpu().pin_memory(), x=torch.from_numpy(x_nb).pin_memory())
+                          ptr=csr.cat_indptr.cpu().pin_memory(), x=torch.from_numpy(sides[side]["x_np"]).pin_memory())
         h2d += sum(t.numel() * t.element_size() for t in host[side].values())
 
     def step():
@@ -400,13 +452,16 @@ def run_e2e(args, wl, sides, dev, world, barrier):
             h, s = host[side], sides[side]
             ep, sup, ptr = (h[k].to(dev, non_blocking=True) for k in ("ep", "sup", "ptr"))
             x = h["x"].to(dev, non_blocking=True).requires_grad_(True)
-            csr = MultiLinkCSR.from_device(ep, sup, ptr, R, s["n_dst"], x.shape[0])
+            csr = MultiLinkCSR.from_device(ep, sup, ptr, R, s["n_dst"], s["csr"].n_nb)
             for p in s["agg"].parameters():
                 p.grad = None
-            out = s["agg"](x, csr)
+            xin = x if s["plan"] is None else sgd.halo_exchange(x, s["plan"])
+            out = s["agg"](xin, csr)
             loss = 0.5 * (out * out).mean()
             loss.backward()
             total = total + loss.detach()
+        if world > 1:
+            sgd.allreduce_grads(all_params)
         return float(total.item())   # D2H read of the step's result
 
     steps = max(3, min(args.steps, 10))
@@ -425,10 +480,10 @@ def run_e2e(args, wl, sides, dev, world, barrier):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    edges = sum(s["csr"].nnz for s in sides.values())
-    return dict(value=edges * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
+    return dict(value=total_edges / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=4, includes="H2D of CSR+features from pinned memory, device plan rebuild "
-                "(transpose + schedules), fwd+bwd, scalar loss read-back")
+                "(transpose + schedules), " + ("halo exchange, " if world > 1 else "") + "fwd+bwd, scalar loss read-back"
+                + ("; per rank, halo index plan reused" if world > 1 else ""))
 
 
 def main():

@@ -1,0 +1,106 @@
+"""Host-side logic of the node-partitioned path (star-gcn_b200/dist.py), world_size 2 and 3 over gloo on
+CPU tensors: partition ranges, halo index plans (who fetches which rows), column rewriting, and the
+consistency of the synthetic partitioned workload.  The row traffic itself (CUDA kernels + NCCL) is
+covered by tests/test_dist_gpu.py and bench.py --gpus N."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _small_base(seed=0):
+    from stargcn_b200 import synth
+    return synth.make_bipartite(60, 40, 700, n_levels=5, seed=seed)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stargcn_b200 import dist as sgd
+        base = _small_base()
+        part = sgd.partitioned_layer_inputs(base, rank, world)
+        rs = np.random.RandomState(1)
+        x_item_global = rs.normal(size=(world * base["n_item"], 8)).astype(np.float32)   # same on every rank
+        x_user_global = rs.normal(size=(world * base["n_user"], 8)).astype(np.float32)
+        res = {}
+        for side, ranges, xg in (("user", part["item_ranges"], x_item_global), ("item", part["user_ranges"], x_user_global)):
+            indptr, cols, vals, sup = part[side]
+            plan = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu")
+            lo, hi = ranges[rank], ranges[rank + 1]
+            x_local = torch.from_numpy(xg[lo:hi])
+            # row exchange emulated with a gloo all-to-all on CPU tensors (test stand-in for pack kernel + NCCL)
+            send_cat = np.concatenate(plan.send_idx) if sum(plan.send_counts) else np.zeros(0, np.int64)
+            send = x_local[torch.from_numpy(send_cat.astype(np.int64))]
+            halo = torch.empty((plan.n_halo, 8))
+            dist.all_to_all_single(halo, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts)
+            x_ext = torch.cat([x_local, halo]).numpy()
+            ok_rows = np.array_equal(x_ext[plan.local_cols], xg[cols])          # rewritten ids address the right rows
+            ok_sorted = all(np.all(np.diff(r) > 0) for r in plan.recv_ids if r.size > 1)
+            res[side] = dict(ok_rows=bool(ok_rows), ok_sorted=bool(ok_sorted), n_halo=plan.n_halo, n_local=plan.n_local,
+                             send_counts=plan.send_counts, recv_counts=plan.recv_counts, nnz=int(cols.size),
+                             edges=set(zip(np.repeat(np.arange(len(indptr) - 1) + (part["user_ranges"] if side == "user" else part["item_ranges"])[rank],
+                                                     np.diff(indptr)).tolist(), cols.tolist())))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_plan_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        for side in ("user", "item"):
+            assert out[r][side]["ok_rows"] and out[r][side]["ok_sorted"]
+            # what r sends to q is what q receives from r
+            for qq in range(world):
+                assert out[r][side]["send_counts"][qq] == out[qq][side]["recv_counts"][r]
+            assert out[r][side]["send_counts"][r] == 0
+    # the two directions describe the same global edge set
+    user_edges = set().union(*[out[r]["user"]["edges"] for r in range(world)])
+    item_edges = set().union(*[{(u, i) for (i, u) in out[r]["item"]["edges"]} for r in range(world)])
+    assert user_edges == item_edges
+    base = _small_base()
+    assert len(user_edges) == world * base["nnz"]
+
+
+def test_ranges():
+    from stargcn_b200 import dist as sgd
+    r = sgd.contiguous_ranges(10, 3)
+    assert r[0] == 0 and r[-1] == 10 and np.all(np.diff(r) >= 3)
+    deg = np.array([100, 1, 1, 1, 1, 100, 1, 1])
+    b = sgd.balanced_ranges(deg, 2)
+    assert b[0] == 0 and b[-1] == 8
+    left = deg[:b[1]].sum()
+    assert abs(left - deg.sum() / 2) <= 100
+
+
+def test_halo_plan_single_rank_is_identity():
+    from stargcn_b200 import dist as sgd
+    cols = np.array([3, 1, 1, 0, 2], np.int64)
+    plan = sgd.HaloPlan(cols, np.array([0, 4]), 0, 1)
+    assert plan.n_halo == 0 and plan.n_local == 4
+    assert np.array_equal(plan.local_cols, cols.astype(np.int32))
+    with pytest.raises(ValueError):
+        sgd.HaloPlan(np.array([5]), np.array([0, 4]), 0, 1)
