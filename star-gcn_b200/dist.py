@@ -118,12 +118,14 @@ class HaloPlan:
         return self
 
     def send_pattern(self):
-        """CSR pattern (one edge per send slot) whose stable transpose sums returned halo gradients."""
+        """CSR pattern with one edge per send slot, built once: forward = pack the requested rows,
+        stable transpose = sum the halo gradients that come back."""
         d = self._dev
         if d["pattern"] is None:
             n = d["send_cat"].numel()
             d["pattern"] = seg_op.CSRPattern(d["send_cat"], torch.arange(n + 1, dtype=torch.int32, device=d["device"]),
-                                             self.n_local)
+                                             self.n_local, use_schedule=False)
+            d["ones"] = torch.ones((1, n), dtype=torch.float32, device=d["device"])
         return d["pattern"]
 
     @property
@@ -147,14 +149,15 @@ class _HaloExchange(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_local, plan):
-        from .decoder import take_rows
         d = plan._dev
         D = x_local.shape[1]
         x_ext = torch.empty((plan.n_ext, D), dtype=torch.float32, device=x_local.device)
         x_ext[:plan.n_local].copy_(x_local)
         if plan.world > 1:
-            send = take_rows(x_local.detach(), d["send_cat"]) if d["send_cat"].numel() else \
-                torch.empty((0, D), dtype=torch.float32, device=x_local.device)
+            if d["send_cat"].numel():   # pack: one gather launch over the cached one-edge-per-slot pattern
+                send = seg_op._seg_pool_fwd(x_local.unsqueeze(0), plan.send_pattern(), "sum")[0][0]
+            else:
+                send = torch.empty((0, D), dtype=torch.float32, device=x_local.device)
             _a2a_rows(x_ext[plan.n_local:], send, plan.recv_counts, plan.send_counts, plan.group)
         ctx.plan, ctx.D = plan, D
         return x_ext
@@ -162,14 +165,14 @@ class _HaloExchange(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ext):
         plan, D = ctx.plan, ctx.D
-        g_local = g_ext[:plan.n_local].contiguous().clone()
+        g_local = g_ext[:plan.n_local].clone()
         if plan.world > 1:
             n_send = sum(plan.send_counts)
             g_back = torch.empty((n_send, D), dtype=torch.float32, device=g_ext.device)
             _a2a_rows(g_back, g_ext[plan.n_local:].contiguous(), plan.send_counts, plan.recv_counts, plan.group)
             if n_send:
-                ones = torch.ones((1, n_send), dtype=torch.float32, device=g_ext.device)
-                seg_op._weighted_pool_bwd_data(g_back.unsqueeze(0), ones, plan.send_pattern(), plan.n_local,
+                pat = plan.send_pattern()
+                seg_op._weighted_pool_bwd_data(g_back.unsqueeze(0), plan._dev["ones"], pat, plan.n_local,
                                                out=g_local.unsqueeze(0), req="add")
         return g_local, None
 

@@ -240,8 +240,9 @@ class _FusedAggTransform(torch.autograd.Function):
     gather.  w_ext [U, R*D + R] = [W_0 | ... | W_{R-1} | b_0 ... b_{R-1}]."""
 
     @staticmethod
-    def forward(ctx, x, w_ext, csr, slope):
+    def forward(ctx, x, w_ext, csr, slope, grad_group=None):
         lib = _lib.load()
+        ctx.grad_group = grad_group
         n_nb, D = x.shape
         R, n_dst = csr.R, csr.n_dst
         U, Kx = w_ext.shape
@@ -285,6 +286,26 @@ class _FusedAggTransform(torch.autograd.Function):
         check(lib.sg_act_bwd_split(_p(gz_hi), _p(gz_lo), ldz, _p(gout), _p(out), n_dst, U, ctypes.c_float(slope),
                                    _stream()), "sg_act_bwd_split")
         gx = gw = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros((U, Kx), dtype=torch.float32, device=dev) if n_dst == 0 else \
+                torch.empty((U, Kx), dtype=torch.float32, device=dev)
+            if n_dst > 0:
+                tiles = ((U + 127) // 128) * ((Kx + 255) // 256)
+                kb = (n_dst + 31) // 32
+                splits = max(1, min(_sm_count(dev) // tiles, kb // 4))
+                e0 = _prof_begin()
+                _gemm_tf32x3(gw, gz_hi, gz_lo, agg_hi, agg_lo, U, Kx, n_dst, mn_major=True, splits=splits)
+                _prof_end("gemm_dw", e0, csr)
+            if ctx.grad_group is not None:
+                # partitioned run: sum the packed weight gradient over ranks here, ONE collective per layer
+                # direction, issued before the transposed gather so NCCL overlaps it
+                import torch.distributed as dist
+                if dist.get_backend(ctx.grad_group) == "nccl":
+                    dist.all_reduce(gw, group=ctx.grad_group)
+                else:
+                    host = gw.cpu()
+                    dist.all_reduce(host, group=ctx.grad_group)
+                    gw.copy_(host)
         if ctx.needs_input_grad[0]:
             gx = torch.empty((n_nb, D), dtype=torch.float32, device=dev)
             if n_dst > 0:
@@ -306,20 +327,10 @@ class _FusedAggTransform(torch.autograd.Function):
             check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, n_dst, n_nb, csr.nnz,
                                            D, 1, plan, chunk, pp, _stream()), "sg_multilink_agg_bwd")
             _prof_end("agg_bwd", e0, csr)
-        if ctx.needs_input_grad[1]:
-            gw = torch.zeros((U, Kx), dtype=torch.float32, device=dev) if n_dst == 0 else \
-                torch.empty((U, Kx), dtype=torch.float32, device=dev)
-            if n_dst > 0:
-                tiles = ((U + 127) // 128) * ((Kx + 255) // 256)
-                kb = (n_dst + 31) // 32
-                splits = max(1, min(_sm_count(dev) // tiles, kb // 4))
-                e0 = _prof_begin()
-                _gemm_tf32x3(gw, gz_hi, gz_lo, agg_hi, agg_lo, U, Kx, n_dst, mn_major=True, splits=splits)
-                _prof_end("gemm_dw", e0, csr)
-        return gx, gw, None, None
+        return gx, gw, None, None, None
 
 
-def fused_agg_transform(x, w_ext, csr, slope):
+def fused_agg_transform(x, w_ext, csr, slope, grad_group=None):
     """act([agg | wsum] . w_ext^T) with act = leaky(slope) (slope 1.0 = identity, 0.0 = ReLU)."""
     if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
         raise TypeError("x must be a 2-D float32 CUDA tensor")
@@ -327,7 +338,7 @@ def fused_agg_transform(x, w_ext, csr, slope):
         raise ValueError(f"x has {x.shape[0]} rows but the plan indexes {csr.n_nb} neighbour rows")
     if x.shape[1] not in FUSED_DIMS:
         raise ValueError(f"the fused path needs D in {FUSED_DIMS}")
-    return _FusedAggTransform.apply(x.contiguous(), w_ext, csr, float(slope))
+    return _FusedAggTransform.apply(x.contiguous(), w_ext, csr, float(slope), grad_group)
 
 
 def multilink_aggregate(x, csr):

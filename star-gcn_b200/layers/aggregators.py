@@ -52,6 +52,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
             assert units % num_links == 0, "units should be divisible by the num_links "
             self._units = self._units // num_links
         self.reference_order = reference_order
+        self.grad_group = None     # torch.distributed group: all-reduce the weight gradient inside backward
         self.tensor_cores = True   # False: fp32 cuBLAS transform after the fused gather (A/B comparison)
         self.dropout = nn.Dropout(dropout_rate)
         # parameters are named weight{i} / bias{i} as in the reference (aggregators.py:86-97)
@@ -130,7 +131,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
         if (self._accum == "sum" or self._num_links == 1) and D in FUSED_DIMS and code is not None and self.tensor_cores:
             # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
             w_ext = torch.cat(ws + [torch.stack(bs, dim=1)], dim=1)   # (U, R*D + R)
-            return fused_agg_transform(neighbor_data, w_ext, csr, {0: 1.0, 1: 0.1, 2: 0.0}[code])
+            return fused_agg_transform(neighbor_data, w_ext, csr, {0: 1.0, 1: 0.1, 2: 0.0}[code], self.grad_group)
         agg, wsum = multilink_aggregate(neighbor_data, csr)           # (n_dst, R*D), (n_dst, R)
         if self._accum == "sum" or self._num_links == 1:
             w_cat = torch.cat(ws, dim=1)                              # (U, R*D)
