@@ -227,6 +227,39 @@ size_t sg_colsum_ws_bytes(int N);
 int sg_colsum(float *out /*N*/, const float *x_hi, const float *x_lo, int M, int N, int ld, void *ws,
               sg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Next rows  device-side neighbour sampling, per-level split and support
+ * replaces CSRMat.sample_neighbors (mxgraph/graph.py:677-748) and the GraphSampler functions it
+ * calls; the whole-graph CSR (ind_ptr, end_points, values) stays resident on the device.
+ * ---------------------------------------------------------------------------------------- */
+/* get_support (GraphSampler/graph_sampler.cpp:393-420): sqrt(1/d_row/d_col) (symm) or 1/d_row;
+ * 0 where a degree is 0.  Bit-exact with the host code (IEEE division / square root). */
+int sg_csr_support(float *support /*nnz*/, const int32_t *row_degrees, const int32_t *col_degrees,
+                   const int32_t *indptr, const int32_t *end_points, int n_rows, int nnz, int symm,
+                   sg_stream_t stream);
+/* scratch for the two calls below (n_sel rows, R levels; R = 1 for the count call) */
+size_t sg_sampler_ws_bytes(int n_sel, int R);
+/* GraphSampler::random_sample_fix_neighbor (graph_sampler.cpp:742-779), step 1:
+ * dst_indptr[i+1] - dst_indptr[i] = neighbor_num < 0 ? deg : min(neighbor_num, deg) for row sel[i]
+ * (sel == NULL: every row); dst_indptr has n_sel + 1 entries, the last one is the sampled nnz. */
+int sg_sample_neighbors_count(int32_t *dst_indptr, const int32_t *src_indptr, const int32_t *sel, int n_sel,
+                              int neighbor_num /* < 0: all, else <= 256 */, void *ws, sg_stream_t stream);
+/* step 2: positions on the nnz axis of the source CSR.  Rows whose quota equals their degree get
+ * p_begin..p_end-1 in order (bit-exact); the others a partial Fisher-Yates draw without replacement
+ * (uniform_choice_range, graph_sampler.cpp:698-732) from a generator keyed by (seed, source row, draw). */
+int sg_sample_neighbors_fill(int32_t *sampled /*nnz_s*/, const int32_t *dst_indptr, const int32_t *src_indptr,
+                             const int32_t *sel, int n_sel, unsigned long long seed, sg_stream_t stream);
+/* multi_link_split_by_value (graph_sampler.cpp:277-312) + the np.take calls of graph.py:725-745, written
+ * relation-major (segment r * n_sel + i):
+ *   cat_indptr [R*n_sel + 1]   ind_ptr of level r, row i = cat_indptr[r*n_sel + i] - cat_indptr[r*n_sel]
+ *   split_index[nnz_s]         position on the SAMPLED axis of every output edge (may be NULL)
+ *   ep_cat / sup_cat / val_cat end point index, support, edge value of every output edge (sup/val may be NULL)
+ *   bad_flag                   set to 1 if an edge value is not in possible_values (the reference ASSERTs) */
+int sg_multilink_split(int32_t *cat_indptr, int32_t *split_index, int32_t *ep_cat, float *sup_cat, float *val_cat,
+                       int32_t *bad_flag, const float *values, const int32_t *end_points, const float *support,
+                       const int32_t *sampled, const int32_t *dst_indptr, const float *possible_values, int R,
+                       int n_sel, void *ws, sg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

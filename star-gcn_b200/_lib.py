@@ -45,6 +45,11 @@ SIGNATURES = {
     "sg_gemm_split_ws_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "sg_gemm_tf32x3": (_c_int, [_c_p, _c_int, _c_p, _c_p, _c_int, _c_p, _c_p, _c_int] + [_c_int] * 5 +
                        [ctypes.c_float, _c_p, _c_int, _c_p, _c_p]),
+    "sg_csr_support": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
+    "sg_sampler_ws_bytes": (_c_sz, [_c_int, _c_int]),
+    "sg_sample_neighbors_count": (_c_int, [_c_p] * 3 + [_c_int] * 2 + [_c_p, _c_p]),
+    "sg_sample_neighbors_fill": (_c_int, [_c_p] * 4 + [_c_int, ctypes.c_ulonglong, _c_p]),
+    "sg_multilink_split": (_c_int, [_c_p] * 12 + [_c_int] * 2 + [_c_p, _c_p]),
     "sg_masked_embed_fwd": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
     "sg_reduce_ws_bytes": (_c_sz, []),
     "sg_sq_err_fwd": (_c_int, [_c_p, _c_p, _c_p, ctypes.c_longlong, ctypes.c_float, _c_p, _c_p]),

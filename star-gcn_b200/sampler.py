@@ -1,0 +1,109 @@
+"""Device-resident graph + neighbour sampling.
+
+``DeviceCSR`` is the device form of one direction of the reference's ``CSRMat``
+(mxgraph/graph.py:261-316): ``ind_ptr``, ``end_points`` (column indices), ``values`` (ratings),
+``multi_link`` (the possible rating values) and the cached ``support`` (graph.py:414-429).
+``sample_neighbors`` mirrors ``CSRMat.sample_neighbors`` (graph.py:677-748) with
+``use_multi_link=True`` but never leaves the device: its result is the relation-major
+:class:`MultiLinkCSR` the fused aggregation consumes, instead of 4·R numpy arrays that
+``heter_sage`` re-uploads on every call (mxgraph/layers/layers.py:366-377).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .graph import MultiLinkCSR
+from .seg_op import _bytes, _p, _stream
+
+
+def _dev_i32(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device, torch.int32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+
+
+def _dev_f32(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device, torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+
+
+class DeviceCSR:
+    def __init__(self, ind_ptr, end_points, values, multi_link, n_cols, row_degrees=None, col_degrees=None,
+                 support=None, symm=True, device="cuda"):
+        self.device = torch.device(device)
+        self.ind_ptr = _dev_i32(ind_ptr, self.device)
+        self.end_points = _dev_i32(end_points, self.device)
+        self.values = _dev_f32(values, self.device)
+        self.multi_link = _dev_f32(multi_link, self.device)
+        self.n_rows = self.ind_ptr.numel() - 1
+        self.n_cols = int(n_cols)
+        self.nnz = self.end_points.numel()
+        self.R = self.multi_link.numel()
+        if support is not None:
+            self.support = _dev_f32(support, self.device)
+        else:
+            if row_degrees is None or (symm and col_degrees is None):
+                raise ValueError("give either `support` or the degree arrays it is computed from")
+            self.support = self.compute_support(_dev_i32(row_degrees, self.device),
+                                                _dev_i32(col_degrees, self.device) if col_degrees is not None else None, symm)
+
+    def compute_support(self, row_degrees, col_degrees, symm=True):
+        """get_support (GraphSampler/graph_sampler.cpp:393-420), on the device, bit-exact."""
+        out = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.device)[:self.nnz]
+        check(_lib.load().sg_csr_support(_p(out), _p(row_degrees), _p(col_degrees), _p(self.ind_ptr), _p(self.end_points),
+                                         self.n_rows, self.nnz, int(bool(symm)), _stream()), "sg_csr_support")
+        return out
+
+    def sample_positions(self, src_inds=None, num_neighbors=-1, seed=0):
+        """random_sample_fix_neighbor: (sampled positions on the nnz axis, dst_ind_ptr) as device tensors."""
+        lib = _lib.load()
+        sel = None if src_inds is None else _dev_i32(src_inds, self.device)
+        n_sel = self.n_rows if sel is None else sel.numel()
+        k = -1 if num_neighbors is None else int(num_neighbors)
+        dst_indptr = torch.empty(n_sel + 1, dtype=torch.int32, device=self.device)
+        ws = _bytes(lib.sg_sampler_ws_bytes(n_sel, 1), self.device)
+        check(lib.sg_sample_neighbors_count(_p(dst_indptr), _p(self.ind_ptr), _p(sel), n_sel, k, _p(ws), _stream()),
+              "sg_sample_neighbors_count")
+        # upper bound known on the host without a sync: every edge (k < 0) or k per row
+        cap = self.nnz if (k < 0 and sel is None) else None
+        nnz_s = cap if cap is not None else int(dst_indptr[-1].item())
+        sampled = torch.empty(max(nnz_s, 1), dtype=torch.int32, device=self.device)[:nnz_s]
+        check(lib.sg_sample_neighbors_fill(_p(sampled), _p(dst_indptr), _p(self.ind_ptr), _p(sel), n_sel,
+                                           ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), _stream()),
+              "sg_sample_neighbors_fill")
+        return sampled, dst_indptr, n_sel
+
+    def split(self, sampled, dst_indptr, n_sel, want_index=False, want_values=False, check_values=False):
+        """multi_link_split + per-level takes -> (cat_indptr, end_points_cat, support_cat[, split_index, values_cat])."""
+        lib = _lib.load()
+        nnz_s = sampled.numel()
+        R = self.R
+        dev = self.device
+        cat_indptr = torch.empty(R * n_sel + 1, dtype=torch.int32, device=dev)
+        ep_cat = torch.empty(max(nnz_s, 1), dtype=torch.int32, device=dev)[:nnz_s]
+        sup_cat = torch.empty(max(nnz_s, 1), dtype=torch.float32, device=dev)[:nnz_s]
+        split_index = torch.empty(max(nnz_s, 1), dtype=torch.int32, device=dev)[:nnz_s] if want_index else None
+        val_cat = torch.empty(max(nnz_s, 1), dtype=torch.float32, device=dev)[:nnz_s] if want_values else None
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = _bytes(lib.sg_sampler_ws_bytes(n_sel, R), dev)
+        check(lib.sg_multilink_split(_p(cat_indptr), _p(split_index), _p(ep_cat), _p(sup_cat), _p(val_cat), _p(bad),
+                                     _p(self.values), _p(self.end_points), _p(self.support), _p(sampled), _p(dst_indptr),
+                                     _p(self.multi_link), R, n_sel, _p(ws), _stream()), "sg_multilink_split")
+        if check_values and int(bad.item()):
+            raise ValueError("an edge value is not in multi_link (graph_sampler.cpp:303 ASSERT)")
+        return cat_indptr, ep_cat, sup_cat, split_index, val_cat
+
+    def sample_neighbors(self, src_inds=None, num_neighbors=-1, seed=0):
+        """CSRMat.sample_neighbors(use_multi_link=True) -> MultiLinkCSR over the selected rows.
+        End points are column INDICES of this matrix (the reference maps them to node ids and
+        gen_plan maps those back to local indices; with every column present the two coincide)."""
+        sampled, dst_indptr, n_sel = self.sample_positions(src_inds, num_neighbors, seed)
+        cat_indptr, ep_cat, sup_cat, _, _ = self.split(sampled, dst_indptr, n_sel)
+        return MultiLinkCSR.from_device(ep_cat, sup_cat, cat_indptr, self.R, n_sel, self.n_cols)
+
+
+__all__ = ["DeviceCSR"]
