@@ -9,12 +9,13 @@
 // and the kernel accumulates  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  into one fp32 TMEM accumulator
 // (the dropped A_lo.B_lo term is ~2^-22 relative).
 //
-// Kernel shape (one 128 x 256 output tile per CTA, 320 threads):
+// Kernel shape (persistent: one CTA per SM loops over 128 x 256 output tiles, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) -> STAGES-deep smem ring
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
 //               (M=128, N=BN, K=8) from smem descriptors; tcgen05.commit frees the stage
 //   warps 2-9   epilogue: drain each TMEM chain (tcgen05.ld 32x32b.x32) into fp32 register
-//               accumulators, then activation -> global stores
+//               accumulators; at the end of a tile bias + activation and coalesced stores through a
+//               padded smem transpose, while the MMA warp already runs the next tile's chains
 // Operand layouts: K-major (A[M,K], B[N,K] row-major; forward and dAgg) or MN-major (A[K,M],
 // B[K,N] row-major; the weight gradient, whose reduction axis is the node axis) — the latter
 // loads [32 floats x 32 k-rows] swizzle atoms (one TMA box each) and sets the a_major/b_major
@@ -37,6 +38,7 @@ struct GemmArgs {
   int M, N;
   int kb_total;      // number of BK-wide k-blocks
   int kb_per_split;
+  int tiles_m, tiles_n, splits;
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
   const float *bias; // optional [N], added before the activation
@@ -132,11 +134,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Accumulation accuracy: the tensor core adds into its fp32 TMEM accumulator with truncation
 // (measured: a 252-MMA chain at K=650 lands 3.5e-6 relative BELOW the exact magnitude, always
 // toward zero).  To stay an order of magnitude inside the 1e-5 parity bar at any K, a TMEM
-// accumulator only ever holds a chain of kChainVBlocks virtual k-blocks (24 MMAs); the epilogue
+// accumulator only ever holds a chain of kChainKBlocks k-blocks (24 MMAs); the epilogue
 // warps drain it (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest
 // while the MMA warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).
 // ---------------------------------------------------------------------------------------------
-constexpr int kChainVBlocks = 6;  // 2 k-blocks x 3 hi/lo products = 24 MMAs per TMEM chain
+constexpr int kChainKBlocks = 2;  // 2 k-blocks x 3 hi/lo products x 4 = 24 MMAs per TMEM chain
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -150,15 +152,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap map_b_lo,
                                                                       const GemmArgs g) {
   static_assert(BN == 256, "two BN-column accumulators must fill the 512 TMEM columns");
+  // one stage = the four operand tiles of ONE k-block (A_hi, A_lo, B_hi, B_lo), each fetched once and
+  // used by the three hi/lo products
   constexpr int A_BYTES = kBM * kBK * 4;
   constexpr int B_BYTES = BN * kBK * 4;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t IDESC = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
-                             ((MN_MAJOR ? 1u : 0u) << 15) | ((MN_MAJOR ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int STG_FLOATS = 32 * 33;  // per-epilogue-warp transpose tile (padded: conflict-free both ways)
+  constexpr uint32_t IDESC_BASE = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
+                                  ((MN_MAJOR ? 1u : 0u) << 15) | ((MN_MAJOR ? 1u : 0u) << 16) |
+                                  ((uint32_t)(kBM >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
@@ -167,12 +173,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * g.kb_per_split;
-  const int kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-  const int n_v = (kb_end - kb_begin) * 3;  // virtual k-blocks: 3 hi/lo products per k-block
-  const int n_chains = (n_v + kChainVBlocks - 1) / kChainVBlocks;
+  // persistent tile loop: tile -> (n tile fastest, then m tile, then split) so the CTAs that share an
+  // A tile run at the same time and find it in L2
+  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;
+  const int n_tiles = tiles_mn * g.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
@@ -191,113 +195,144 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int v = 0; v < n_v; ++v) {
-        const int s = v % STAGES;
-        const uint32_t ph = (v / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int kb = kb_begin + v / 3, pass = v % 3;  // pass 0: lo.hi  1: hi.lo  2: hi.hi
-        const CUtensorMap *ma = pass == 0 ? &map_a_lo : &map_a_hi;
-        const CUtensorMap *mb = pass == 1 ? &map_b_lo : &map_b_hi;
-        uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
-        if constexpr (MN_MAJOR) {  // one [32 floats x 32 k-rows] swizzle atom per load
+      int v = 0;  // running stage counter across tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int m0 = (rem / tiles_n) * kBM, n0 = (rem % tiles_n) * BN;
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
+          if constexpr (MN_MAJOR) {  // one [32 floats x 32 k-rows] swizzle atom per load
 #pragma unroll
-          for (int a = 0; a < kBM / 32; ++a) tma_load_2d(sa + a * (kBK * 128), ma, &full_bar[s], m0 + a * 32, kb * kBK);
+            for (int a = 0; a < kBM / 32; ++a) {
+              tma_load_2d(sa_hi + a * (kBK * 128), &map_a_hi, &full_bar[s], m0 + a * 32, kb * kBK);
+              tma_load_2d(sa_lo + a * (kBK * 128), &map_a_lo, &full_bar[s], m0 + a * 32, kb * kBK);
+            }
 #pragma unroll
-          for (int a = 0; a < BN / 32; ++a) tma_load_2d(sb + a * (kBK * 128), mb, &full_bar[s], n0 + a * 32, kb * kBK);
-        } else {
-          tma_load_2d(sa, ma, &full_bar[s], kb * kBK, m0);
-          tma_load_2d(sb, mb, &full_bar[s], kb * kBK, n0);
+            for (int a = 0; a < BN / 32; ++a) {
+              tma_load_2d(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], n0 + a * 32, kb * kBK);
+              tma_load_2d(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], n0 + a * 32, kb * kBK);
+            }
+          } else {
+            tma_load_2d(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
+            tma_load_2d(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
+            tma_load_2d(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, n0);
+            tma_load_2d(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int v = 0; v < n_v; ++v) {
-        const int s = v % STAGES;
-        const uint32_t ph = (v / STAGES) & 1;
-        const int chain = v / kChainVBlocks, vin = v - chain * kChainVBlocks;
-        const int buf = chain & 1;
-        if (vin == 0) {  // start of a chain: the epilogue warps must have drained this buffer
-          mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-#pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          uint64_t da, db;
-          if constexpr (MN_MAJOR) {  // boxes [32 floats x 32 k-rows] 4096 B apart (LBO); 4-row swizzle groups
-                                     // 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
-            da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
-            db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
-          } else {                   // rows of 128 B, 8-row groups 1024 B apart; 8 floats = 32 B per MMA
-            da = make_smem_desc(sa + k * 32, 16, 1024, 2);
-            db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+      int v = 0, chain = 0;  // running counters across tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int n0 = (rem % tiles_n) * BN;
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        const int n_kb = kb_end - kb_begin;
+        // UMMA N for this tile: the valid columns rounded up to 16 (a partly empty last n-tile costs less)
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        for (int i = 0; i < n_kb; ++i, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          const int vin = i % kChainKBlocks;
+          const int buf = chain & 1;
+          if (vin == 0) {  // start of a chain: the epilogue warps must have drained this buffer
+            mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            tc_fence_after();
           }
-          umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (vin | k) != 0);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
+                         sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
+            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              uint64_t da, db;
+              if constexpr (MN_MAJOR) {  // boxes [32 floats x 32 k-rows] 4096 B apart (LBO); 4-row swizzle groups
+                                         // 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
+                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
+                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
+              } else {                   // rows of 128 B, 8-row groups 1024 B apart; 8 floats = 32 B per MMA
+                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+              }
+              umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin | pass | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (vin == kChainKBlocks - 1 || i == n_kb - 1) {
+            umma_commit(&tmem_full_bar[buf]);
+            ++chain;
+          }
         }
-        umma_commit(&empty_bar[s]);
-        if (vin == kChainVBlocks - 1 || v == n_v - 1) umma_commit(&tmem_full_bar[buf]);
       }
     }
   } else {
     // epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half h
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
-    const int row = m0 + q * 32 + lane;
     const int cbase = h * (BN / 2);
-    const bool active = n0 + cbase < g.N;  // warp-uniform
-    float racc[BN / 2];
+    float *stg = stg_all + (warp - 2) * STG_FLOATS;
+    const bool v_ok = true;
+    (void)v_ok;
+    int chain = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+      const int m0 = (rem / tiles_n) * kBM, n0 = (rem % tiles_n) * BN;
+      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      const int n_chains = (kb_end - kb_begin + kChainKBlocks - 1) / kChainKBlocks;
+      const bool active = n0 + cbase < g.N;  // warp-uniform
+      float racc[BN / 2];
 #pragma unroll
-    for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
-    for (int chain = 0; chain < n_chains; ++chain) {
-      const int buf = chain & 1;
-      mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
-      tc_fence_after();
+      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
+      for (int c = 0; c < n_chains; ++c, ++chain) {
+        const int buf = chain & 1;
+        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+        tc_fence_after();
+        if (active) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
       if (active) {
+        // thread = row in registers -> 32x32 transpose through padded smem -> lane = column: every store
+        // instruction writes 128 contiguous bytes of one output row
+        float *dbase = g.D + (long long)z * g.split_stride;
+        const int row0 = m0 + q * 32;
 #pragma unroll
         for (int ch = 0; ch < BN / 2 / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
-          tmem_wait_ld();
+          const int col = n0 + cbase + ch * 32 + lane;
+          if (n0 + cbase + ch * 32 >= g.N) break;  // warp-uniform
+          float bias = 0.f;
+          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
+          __syncwarp();
+          const int rows = min(32, g.M - row0);
+          for (int rr = 0; rr < rows; ++rr) {
+            float x = stg[rr * 33 + lane] + bias;
+            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
+            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+          }
+          __syncwarp();
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-    }
-    if (active && row < g.M) {
-      float *drow = g.D + (long long)blockIdx.z * g.split_stride + (long long)row * g.ldd;
-      const bool v4 = (g.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0 && (g.split_stride & 3) == 0;
-      const bool v2 = (g.ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 7) == 0 && (g.split_stride & 1) == 0;
-      const int col = n0 + cbase;
-      if (g.bias) {
-#pragma unroll
-        for (int j = 0; j < BN / 2; ++j)
-          if (col + j < g.N) racc[j] += __ldg(g.bias + col + j);
-      }
-      if (g.epi == 1) {
-#pragma unroll
-        for (int j = 0; j < BN / 2; ++j) racc[j] = racc[j] > 0.f ? racc[j] : g.slope * racc[j];
-      }
-      if (col + BN / 2 <= g.N && v4) {
-#pragma unroll
-        for (int j = 0; j < BN / 2; j += 4)
-          *reinterpret_cast<float4 *>(drow + col + j) = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
-      } else if (v2) {
-#pragma unroll
-        for (int j = 0; j < BN / 2; j += 2) {
-          if (col + j + 1 < g.N) *reinterpret_cast<float2 *>(drow + col + j) = make_float2(racc[j], racc[j + 1]);
-          else if (col + j < g.N) drow[col + j] = racc[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < BN / 2; ++j)
-          if (col + j < g.N) drow[col + j] = racc[j];
       }
     }
   }
@@ -409,14 +444,18 @@ static int make_map_mnmajor(CUtensorMap *m, const float *x, int K, int mn, int l
 }
 
 template <int BN, int STAGES, bool MN>
-static int launch_gemm(const CUtensorMap (&maps)[4], const GemmArgs &g, int splits, cudaStream_t st) {
-  constexpr int smem = STAGES * (kBM * kBK * 4 + BN * kBK * 4) + 1024;
+static int launch_gemm(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<BN, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(g.M, kBM), (unsigned)ceil_div(g.N, BN), (unsigned)splits);
+  g.tiles_m = ceil_div(g.M, kBM);
+  g.tiles_n = ceil_div(g.N, BN);
+  g.splits = splits;
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());  // persistent: one CTA per SM
   tf32x3_gemm_kernel<BN, STAGES, MN><<<grid, kGemmThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
   SG_LAUNCHED("tf32x3_gemm_kernel");
   return SG_OK;
@@ -468,13 +507,13 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
     if ((rc = make_map_mnmajor(&maps[1], A_lo, K, M, lda)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[3], B_lo, K, N, ldb)) != SG_OK) return rc;
-    if ((rc = launch_gemm<256, 4, true>(maps, g, splits, st)) != SG_OK) return rc;
+    if ((rc = launch_gemm<256, 2, true>(maps, g, splits, st)) != SG_OK) return rc;
   } else {
     if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
     if ((rc = make_map_kmajor(&maps[1], A_lo, M, K, lda, kBM)) != SG_OK) return rc;
     if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, BN)) != SG_OK) return rc;
     if ((rc = make_map_kmajor(&maps[3], B_lo, N, K, ldb, BN)) != SG_OK) return rc;
-    if ((rc = launch_gemm<256, 4, false>(maps, g, splits, st)) != SG_OK) return rc;
+    if ((rc = launch_gemm<256, 2, false>(maps, g, splits, st)) != SG_OK) return rc;
   }
   if (splits > 1) {
     splitk_reduce_kernel<<<grid_ew((long long)M * N), 256, 0, st>>>(D, ldd, split_ws, M, N, splits);
