@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -314,14 +315,39 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t)
         total_edges = int(t.item())
 
-    def step():
-        for s in sides.values():
-            s["x"].grad = None
-            for p in s["agg"].parameters():
-                p.grad = None
-            xin = s["x"] if s["plan"] is None else sgd.halo_exchange(s["x"], s["plan"])
-            out = s["agg"](xin, s["csr"])
-            out.backward(s["gout"])
+    from stargcn_b200 import runtime
+    side_streams = [torch.cuda.Stream(device=dev) for _ in sides]
+
+    def one_side(s):
+        s["x"].grad = None
+        for p in s["agg"].parameters():
+            p.grad = None
+        xin = s["x"] if s["plan"] is None else sgd.halo_exchange(s["x"], s["plan"])
+        out = s["agg"](xin, s["csr"])
+        out.backward(s["gout"])
+
+    def eager_step():
+        # the two directions are independent: each on its own stream, so one direction's halo exchange /
+        # tensor-core GEMMs overlap the other's gathers
+        with runtime.fork_join(side_streams) as run:
+            for i, s in enumerate(sides.values()):
+                run(i, lambda s=s: one_side(s))
+
+    step, graphed, launches_per_step = eager_step, False, None
+    if not args.no_graph:
+        try:
+            for _ in range(2):
+                eager_step()                      # first calls build plans / communicators outside the capture
+            torch.cuda.synchronize()
+            _lib.reset_launch_count()
+            eager_step()
+            torch.cuda.synchronize()
+            launches_per_step = _lib.launch_count()
+            step, graphed = runtime.GraphedStep(eager_step), True
+        except Exception as e:                    # capture not possible here: say so and time the eager step
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing the eager step", file=sys.stderr)
+            torch.cuda.synchronize()
+            step, graphed = eager_step, False
 
     # clocks are sampled (rank 0, 50 ms period) from the first warm-up step to the end of the timed region
     sampler = ClockSampler(local_rank)
@@ -332,7 +358,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks ----
-    graph.PROFILE = []
+    if not graphed:
+        graph.PROFILE = []
     _lib.reset_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,8 +368,16 @@ def run_gpu_arm(args, rank, world, local_rank):
         step()
     e1.record()
     barrier()
-    launches = _lib.launch_count()
+    launches = _lib.launch_count() if not graphed else launches_per_step * args.steps
     ms_total = e0.elapsed_time(e1)
+    if graphed:
+        # per-kernel CUDA events cannot be read inside graph replays: time the same kernels on the same buffers
+        # in an eager pass right after the timed region (single stream order, so the events bracket one kernel)
+        graph.PROFILE = []
+        for _ in range(min(args.steps, 20)):
+            for s in sides.values():
+                one_side(s)
+        torch.cuda.synchronize()
     prof, graph.PROFILE = graph.PROFILE, None
     clocks = sampler.stop()
     if world > 1:
@@ -418,6 +453,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                               f"per layer direction one NCCL all-to-all of halo rows fwd + its transpose bwd, all-reduce of weight grads; "
                               f"rank 0 halo = {halo_rows} rows x {D * 4} B per step-direction pair",
                               total_edges_per_step=total_edges,
+                              execution=("one CUDA graph per step (captured once, replayed K times): " if graphed else "eager launches: ") +
+                              "the two directions on two streams",
                               l2="inputs exceed L2: ~%.0f MB of CSR/feature/intermediate traffic per step vs 126 MB L2; no flush" % (
                                   (sum(algorithmic_bytes(s['csr'].nnz, s['csr'].n_seg, s['csr'].n_nb, 0, True) for s in sides.values()) * 2
                                    + sum(s['n_dst'] * (R * D + U) * 4 * 3 for s in sides.values())) / 1e6)),

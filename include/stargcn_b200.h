@@ -260,6 +260,32 @@ int sg_multilink_split(int32_t *cat_indptr, int32_t *split_index, int32_t *ep_ca
                        const int32_t *sampled, const int32_t *dst_indptr, const float *possible_values, int R,
                        int n_sel, void *ws, sg_stream_t stream);
 
+/* Next rows  batch-edge removal: remove_edges (GraphSampler/graph_sampler.cpp:154-201,
+ * called from HeterGraph.remove_edges_by_id, mxgraph/graph.py:952-974, every training iteration at
+ * experiments/STAR-GCN.py:595-600).  Two steps so the caller can size the outputs:
+ *   count: marks every copy of each listed (row, col) pair in ws, writes the new ind_ptr (n_rows + 1;
+ *          the last entry is the new nnz)
+ *   fill:  stable compaction of end_points / values (values may be NULL) using the marks left in ws */
+size_t sg_remove_edges_ws_bytes(int n_rows, int nnz);
+int sg_remove_edges_count(int32_t *dst_indptr, const int32_t *indptr, const int32_t *end_points,
+                          const int32_t *rm_rows, const int32_t *rm_cols, int n_rows, int nnz, int n_rm, void *ws,
+                          sg_stream_t stream);
+int sg_remove_edges_fill(int32_t *dst_end_points, float *dst_values, const int32_t *dst_indptr,
+                         const int32_t *indptr, const int32_t *end_points, const float *values, int n_rows,
+                         int nnz, const void *ws, sg_stream_t stream);
+/* counts[b] = |{i : idx[i] == b}| (column degrees after a removal; np.bincount) */
+int sg_bincount(int32_t *counts /*n_bins*/, const int32_t *idx, int n, int n_bins, sg_stream_t stream);
+
+/* Next rows  unique + inverse in first-occurrence order: the serial unique_inverse of
+ * GraphSampler/graph_sampler.h:510-534 behind merge_nodes (mxgraph/graph.py:142-163), which gen_plan uses to
+ * turn sampled end-point ids into local row indices (mxgraph/layers/layers.py:308-334).
+ *   uniq[0..n_unique)  distinct values in order of first appearance     (capacity n)
+ *   inverse[i]         index into uniq of data[i]                        (n)
+ *   n_unique           device scalar */
+size_t sg_unique_inverse_ws_bytes(int n);
+int sg_unique_inverse(int32_t *uniq, int32_t *inverse, int32_t *n_unique, const int32_t *data, int n, void *ws,
+                      size_t ws_bytes, sg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

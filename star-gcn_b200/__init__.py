@@ -9,6 +9,6 @@ the one-file shim ``stargcn_b200.py`` at the repo root.
     decoder    masked-embedding lookup, reconstruction decoder and losses
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from . import seg_op, graph, layers, decoder, sampler  # noqa: F401
+from . import seg_op, graph, layers, decoder, sampler, runtime  # noqa: F401
 
 __version__ = "0.1.0"

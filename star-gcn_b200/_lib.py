@@ -50,6 +50,12 @@ SIGNATURES = {
     "sg_sample_neighbors_count": (_c_int, [_c_p] * 3 + [_c_int] * 2 + [_c_p, _c_p]),
     "sg_sample_neighbors_fill": (_c_int, [_c_p] * 4 + [_c_int, ctypes.c_ulonglong, _c_p]),
     "sg_multilink_split": (_c_int, [_c_p] * 12 + [_c_int] * 2 + [_c_p, _c_p]),
+    "sg_remove_edges_ws_bytes": (_c_sz, [_c_int, _c_int]),
+    "sg_remove_edges_count": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p, _c_p]),
+    "sg_remove_edges_fill": (_c_int, [_c_p] * 6 + [_c_int] * 2 + [_c_p, _c_p]),
+    "sg_bincount": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_p]),
+    "sg_unique_inverse_ws_bytes": (_c_sz, [_c_int]),
+    "sg_unique_inverse": (_c_int, [_c_p] * 4 + [_c_int, _c_p, _c_sz, _c_p]),
     "sg_masked_embed_fwd": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
     "sg_reduce_ws_bytes": (_c_sz, []),
     "sg_sq_err_fwd": (_c_int, [_c_p, _c_p, _c_p, ctypes.c_longlong, ctypes.c_float, _c_p, _c_p]),

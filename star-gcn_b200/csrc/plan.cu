@@ -217,6 +217,52 @@ __global__ void __launch_bounds__(256) multilink_finish(int32_t *__restrict__ t_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// unique + inverse in FIRST-OCCURRENCE order: the serial, order-defining
+// unique_inverse of GraphSampler/graph_sampler.h:510-534 that merge_nodes / gen_plan use to turn
+// node ids into local row indices (mxgraph/graph.py:142-163, layers.py:308-334).
+//   stable sort (value, position) -> run heads -> rank the runs by the position of their first
+//   element -> unique[rank] = value, inverse[position] = rank.  Integer work, bit-exact.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) run_heads_kernel(int32_t *__restrict__ head, const int32_t *__restrict__ ks, int n) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    head[j] = (j == 0 || ks[j] != ks[j - 1]) ? 1 : 0;
+}
+
+// run_of[j] = index of the run sorted element j belongs to; first_pos[run] = original position of its head
+__global__ void __launch_bounds__(256) run_first_pos_kernel(int32_t *__restrict__ first_pos, int32_t *__restrict__ run_iota,
+                                                            const int32_t *__restrict__ head_excl,
+                                                            const int32_t *__restrict__ ks, const int32_t *__restrict__ pos,
+                                                            int n) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    if (j == 0 || ks[j] != ks[j - 1]) {
+      const int u = head_excl[j];
+      first_pos[u] = pos[j];
+      run_iota[u] = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rank_scatter_kernel(int32_t *__restrict__ rank, const int32_t *__restrict__ order,
+                                                           const int32_t *__restrict__ n_unique) {
+  const int n = *n_unique;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) rank[order[k]] = k;
+}
+
+__global__ void __launch_bounds__(256) unique_write_kernel(int32_t *__restrict__ uniq, int32_t *__restrict__ inverse,
+                                                           const int32_t *__restrict__ rank,
+                                                           const int32_t *__restrict__ head_excl,
+                                                           const int32_t *__restrict__ ks, const int32_t *__restrict__ pos,
+                                                           int n) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const bool is_head = j == 0 || ks[j] != ks[j - 1];
+    const int u = head_excl[j] + (is_head ? 0 : -1);  // exclusive count of heads before j; non-heads belong to the previous head
+    const int r = rank[u];
+    if (is_head) uniq[r] = ks[j];
+    inverse[pos[j]] = r;
+  }
+}
+
 static inline int grid_for(long long n, int threads = 256) {
   long long g = ceil_div<long long>(n > 0 ? n : 1, threads);
   long long cap = (long long)num_sms() * 32;
@@ -355,6 +401,69 @@ int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_p
   SG_REQUIRE(t_src && t_w && t_perm && t_seg && support, "sg_multilink_transpose_finish: null pointer");
   multilink_finish<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(t_src, t_w, t_perm, t_seg, support, R, n_dst, nnz);
   SG_LAUNCHED("multilink_finish");
+  return SG_OK;
+}
+
+size_t sg_unique_inverse_ws_bytes(int n) {
+  if (n <= 0) return 64;
+  size_t cub_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                                  (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
+  if (e != cudaSuccess) {
+    sg::fail(SG_ERR_CUDA, "sg_unique_inverse_ws_bytes: CUB size query failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return 8 * align_up((size_t)n * sizeof(int32_t), 256) + align_up(cub_bytes, 256) + scan_ws_bytes(n) + 512;
+}
+
+int sg_unique_inverse(int32_t *uniq, int32_t *inverse, int32_t *n_unique, const int32_t *data, int n, void *ws,
+                      size_t ws_bytes, sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(n >= 0, "sg_unique_inverse: negative size");
+  SG_REQUIRE(n_unique, "sg_unique_inverse: null n_unique");
+  if (n == 0) { SG_CUDA(cudaMemsetAsync(n_unique, 0, sizeof(int32_t), st)); return SG_OK; }
+  SG_REQUIRE(uniq && inverse && data && ws, "sg_unique_inverse: null pointer");
+  const size_t need = sg_unique_inverse_ws_bytes(n);
+  if (need == 0) return SG_ERR_CUDA;
+  if (ws_bytes < need) return sg::fail(SG_ERR_WORKSPACE, "sg_unique_inverse: workspace %zu < %zu bytes", ws_bytes, need);
+  const size_t stride = align_up((size_t)n * sizeof(int32_t), 256);
+  char *base = static_cast<char *>(ws);
+  int32_t *iota = reinterpret_cast<int32_t *>(base);
+  int32_t *ks = reinterpret_cast<int32_t *>(base + stride);
+  int32_t *pos = reinterpret_cast<int32_t *>(base + 2 * stride);
+  int32_t *head = reinterpret_cast<int32_t *>(base + 3 * stride);
+  int32_t *first_pos = reinterpret_cast<int32_t *>(base + 4 * stride);
+  int32_t *run_iota = reinterpret_cast<int32_t *>(base + 5 * stride);
+  int32_t *fp_sorted = reinterpret_cast<int32_t *>(base + 6 * stride);
+  int32_t *order = reinterpret_cast<int32_t *>(base + 7 * stride);
+  void *cub_ws = base + 8 * stride;
+  size_t cub_bytes = 0;
+  SG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                          (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32));
+  void *scan_ws = static_cast<char *>(cub_ws) + align_up(cub_bytes, 256);
+  int32_t *rank = head;  // head[] is dead once its scan (in place, exclusive) has been consumed... keep separate: reuse iota
+  iota_kernel<<<grid_for(n), 256, 0, st>>>(iota, n);
+  SG_LAUNCHED("iota_kernel");
+  SG_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, data, ks, (const int32_t *)iota, pos, n, 0, 32, st));
+  sg::count_launch(4);
+  run_heads_kernel<<<grid_for(n), 256, 0, st>>>(head, ks, n);
+  SG_LAUNCHED("run_heads_kernel");
+  int rc = exclusive_scan_i32(head, head, n, n_unique, scan_ws, st);  // head[j] := number of heads before j
+  if (rc != SG_OK) return rc;
+  // sentinel first positions (INT_MAX) for the unused tail so that the second sort keeps real runs in front
+  SG_CUDA(cudaMemsetAsync(first_pos, 0x7f, stride, st));
+  SG_CUDA(cudaMemsetAsync(run_iota, 0, stride, st));
+  run_first_pos_kernel<<<grid_for(n), 256, 0, st>>>(first_pos, run_iota, head, ks, pos, n);
+  SG_LAUNCHED("run_first_pos_kernel");
+  SG_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, (const int32_t *)first_pos, fp_sorted,
+                                          (const int32_t *)run_iota, order, n, 0, 32, st));
+  sg::count_launch(4);
+  rank = iota;  // iota[] is no longer needed
+  rank_scatter_kernel<<<grid_for(n), 256, 0, st>>>(rank, order, n_unique);
+  SG_LAUNCHED("rank_scatter_kernel");
+  unique_write_kernel<<<grid_for(n), 256, 0, st>>>(uniq, inverse, rank, head, ks, pos, n);
+  SG_LAUNCHED("unique_write_kernel");
   return SG_OK;
 }
 

@@ -180,6 +180,82 @@ __global__ void __launch_bounds__(256) level_scatter_kernel(int32_t *__restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// batch-edge removal: remove_edges, GraphSampler/graph_sampler.cpp:154-201 — the
+// reference rebuilds both CSR directions on ONE host thread every training iteration
+// (experiments/STAR-GCN.py:595-600).  Here: mark (one warp per removal pair scans its row),
+// count kept edges per row, scan, stable compaction (one warp per row, ballot).  Order inside
+// rows is preserved, every copy of a listed (row, col) pair is dropped: bit-exact outputs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mark_removed_kernel(int32_t *__restrict__ keep, const int32_t *__restrict__ indptr,
+                                                           const int32_t *__restrict__ end_points,
+                                                           const int32_t *__restrict__ rm_rows,
+                                                           const int32_t *__restrict__ rm_cols, int n_rows, int n_rm) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = warp; e < n_rm; e += n_warps) {
+    const int r = __ldg(rm_rows + e), c = __ldg(rm_cols + e);
+    if (r < 0 || r >= n_rows) continue;
+    for (int p = __ldg(indptr + r) + lane; p < __ldg(indptr + r + 1); p += 32)
+      if (__ldg(end_points + p) == c) keep[p] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) count_kept_kernel(int32_t *__restrict__ counts, const int32_t *__restrict__ keep,
+                                                         const int32_t *__restrict__ indptr, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n_rows; i += n_warps) {
+    int c = 0;
+    for (int p = __ldg(indptr + i) + lane; p < __ldg(indptr + i + 1); p += 32) c += __ldg(keep + p) != 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) counts[i] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) compact_rows_kernel(int32_t *__restrict__ dst_ep, float *__restrict__ dst_val,
+                                                           const int32_t *__restrict__ dst_indptr,
+                                                           const int32_t *__restrict__ keep,
+                                                           const int32_t *__restrict__ end_points,
+                                                           const float *__restrict__ values,
+                                                           const int32_t *__restrict__ indptr, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i = warp; i < n_rows; i += n_warps) {
+    const int lo = __ldg(indptr + i), hi = __ldg(indptr + i + 1);
+    int out = __ldg(dst_indptr + i);
+    for (int base = lo; base < hi; base += 32) {
+      const int p = base + lane;
+      const bool k = p < hi && __ldg(keep + p) != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (k) {
+        const int o = out + __popc(m & lt);
+        dst_ep[o] = __ldg(end_points + p);
+        if (dst_val) dst_val[o] = __ldg(values + p);
+      }
+      out += __popc(m);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *__restrict__ out, int v, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = v;
+}
+
+// integer histogram (degrees of the column side); integer atomics: the result is order-independent
+__global__ void __launch_bounds__(256) bincount_kernel(int32_t *__restrict__ counts, const int32_t *__restrict__ idx, int n,
+                                                       int n_bins) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = __ldg(idx + i);
+    if (b >= 0 && b < n_bins) atomicAdd(counts + b, 1);
+  }
+}
+
 static inline int grid_w(long long n_warps_needed) {
   long long g = ceil_div<long long>(n_warps_needed > 0 ? n_warps_needed : 1, 8);
   long long cap = (long long)num_sms() * 16;
@@ -250,6 +326,56 @@ int sg_multilink_split(int32_t *cat_indptr, int32_t *split_index, int32_t *ep_ca
   level_scatter_kernel<<<grid_w(n_sel), 256, 0, st>>>(split_index, ep_cat, sup_cat, val_cat, cat_indptr, values, end_points, support,
                                                       sampled, dst_indptr, possible_values, R, n_sel);
   SG_LAUNCHED("level_scatter_kernel");
+  return SG_OK;
+}
+
+size_t sg_remove_edges_ws_bytes(int n_rows, int nnz) {
+  return align_up((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t), 64) + scan_ws_bytes(n_rows > 0 ? n_rows : 1) + 128;
+}
+
+int sg_remove_edges_count(int32_t *dst_indptr, const int32_t *indptr, const int32_t *end_points, const int32_t *rm_rows,
+                          const int32_t *rm_cols, int n_rows, int nnz, int n_rm, void *ws, sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(n_rows >= 0 && nnz >= 0 && n_rm >= 0, "sg_remove_edges_count: negative size");
+  SG_REQUIRE(dst_indptr && ws && (n_rows == 0 || indptr), "sg_remove_edges_count: null pointer");
+  if (n_rows == 0) { SG_CUDA(cudaMemsetAsync(dst_indptr, 0, sizeof(int32_t), st)); return SG_OK; }
+  int32_t *keep = static_cast<int32_t *>(ws);
+  void *scan_ws = static_cast<char *>(ws) + align_up((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t), 64);
+  if (nnz > 0) {
+    SG_REQUIRE(end_points && (n_rm == 0 || (rm_rows && rm_cols)), "sg_remove_edges_count: null pointer");
+    fill_i32_kernel<<<grid_w(ceil_div(nnz, 32)), 256, 0, st>>>(keep, 1, nnz);
+    SG_LAUNCHED("fill_i32_kernel");
+    if (n_rm > 0) {
+      mark_removed_kernel<<<grid_w(n_rm), 256, 0, st>>>(keep, indptr, end_points, rm_rows, rm_cols, n_rows, n_rm);
+      SG_LAUNCHED("mark_removed_kernel");
+    }
+  }
+  count_kept_kernel<<<grid_w(n_rows), 256, 0, st>>>(dst_indptr, keep, indptr, n_rows);
+  SG_LAUNCHED("count_kept_kernel");
+  return exclusive_scan_i32(dst_indptr, dst_indptr, n_rows, dst_indptr + n_rows, scan_ws, st);
+}
+
+int sg_remove_edges_fill(int32_t *dst_end_points, float *dst_values, const int32_t *dst_indptr, const int32_t *indptr,
+                         const int32_t *end_points, const float *values, int n_rows, int nnz, const void *ws,
+                         sg_stream_t stream) {
+  SG_REQUIRE(n_rows >= 0 && nnz >= 0, "sg_remove_edges_fill: negative size");
+  if (n_rows == 0 || nnz == 0) return SG_OK;
+  SG_REQUIRE(dst_end_points && dst_indptr && indptr && end_points && ws && (!dst_values || values), "sg_remove_edges_fill: null pointer");
+  compact_rows_kernel<<<grid_w(n_rows), 256, 0, (cudaStream_t)stream>>>(dst_end_points, dst_values, dst_indptr,
+                                                                        static_cast<const int32_t *>(ws), end_points, values, indptr, n_rows);
+  SG_LAUNCHED("compact_rows_kernel");
+  return SG_OK;
+}
+
+int sg_bincount(int32_t *counts, const int32_t *idx, int n, int n_bins, sg_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SG_REQUIRE(n >= 0 && n_bins >= 0, "sg_bincount: negative size");
+  if (n_bins == 0) return SG_OK;
+  SG_REQUIRE(counts && (n == 0 || idx), "sg_bincount: null pointer");
+  SG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_bins, st));
+  if (n == 0) return SG_OK;
+  bincount_kernel<<<grid_w(ceil_div(n, 32)), 256, 0, st>>>(counts, idx, n, n_bins);
+  SG_LAUNCHED("bincount_kernel");
   return SG_OK;
 }
 

@@ -58,6 +58,32 @@ class DeviceCSR:
                                          self.n_rows, self.nnz, int(bool(symm)), _stream()), "sg_csr_support")
         return out
 
+    def remove_edges(self, rm_rows, rm_cols, symm=True, col_degrees=None):
+        """CSRMat.remove_edges_by_ind (mxgraph/graph.py:631-658 -> graph_sampler.cpp:154-201): a new DeviceCSR
+        without the listed (row index, column index) pairs; order inside rows is preserved.  The support is
+        recomputed from the new degrees (``col_degrees``: degrees of the column side after the removal —
+        the row degrees of the reverse matrix; computed here with a histogram when not given)."""
+        lib = _lib.load()
+        dev = self.device
+        rr, rc = _dev_i32(rm_rows, dev), _dev_i32(rm_cols, dev)
+        if rr.numel() != rc.numel():
+            raise ValueError("rm_rows and rm_cols must have the same length")
+        ws = _bytes(lib.sg_remove_edges_ws_bytes(self.n_rows, self.nnz), dev)
+        new_ptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+        check(lib.sg_remove_edges_count(_p(new_ptr), _p(self.ind_ptr), _p(self.end_points), _p(rr), _p(rc), self.n_rows,
+                                        self.nnz, rr.numel(), _p(ws), _stream()), "sg_remove_edges_count")
+        new_nnz = int(new_ptr[-1].item())
+        new_ep = torch.empty(max(new_nnz, 1), dtype=torch.int32, device=dev)[:new_nnz]
+        new_val = torch.empty(max(new_nnz, 1), dtype=torch.float32, device=dev)[:new_nnz]
+        check(lib.sg_remove_edges_fill(_p(new_ep), _p(new_val), _p(new_ptr), _p(self.ind_ptr), _p(self.end_points),
+                                       _p(self.values), self.n_rows, self.nnz, _p(ws), _stream()), "sg_remove_edges_fill")
+        row_deg = new_ptr[1:] - new_ptr[:-1]
+        if symm and col_degrees is None:
+            col_degrees = torch.empty(self.n_cols, dtype=torch.int32, device=dev)
+            check(lib.sg_bincount(_p(col_degrees), _p(new_ep), new_nnz, self.n_cols, _stream()), "sg_bincount")
+        return DeviceCSR(new_ptr, new_ep, new_val, self.multi_link, self.n_cols, row_degrees=row_deg.contiguous(),
+                         col_degrees=col_degrees, symm=symm, device=dev)
+
     def sample_positions(self, src_inds=None, num_neighbors=-1, seed=0):
         """random_sample_fix_neighbor: (sampled positions on the nnz axis, dst_ind_ptr) as device tensors."""
         lib = _lib.load()
@@ -106,4 +132,37 @@ class DeviceCSR:
         return MultiLinkCSR.from_device(ep_cat, sup_cat, cat_indptr, self.R, n_sel, self.n_cols)
 
 
-__all__ = ["DeviceCSR"]
+def unique_inverse(data):
+    """(unique values in first-occurrence order, inverse indices) of an int32 device tensor — the serial
+    ``unique_inverse`` (GraphSampler/graph_sampler.h:510-534) that ``merge_nodes`` relies on."""
+    lib = _lib.load()
+    if not isinstance(data, torch.Tensor) or not data.is_cuda or data.dtype != torch.int32 or data.dim() != 1:
+        raise TypeError("data must be a 1-D int32 CUDA tensor")
+    data = data.contiguous()
+    n = data.numel()
+    dev = data.device
+    uniq = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+    n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.sg_unique_inverse_ws_bytes(n)
+    if ws_bytes == 0:
+        check(2, "sg_unique_inverse_ws_bytes")
+    ws = _bytes(ws_bytes, dev)
+    check(lib.sg_unique_inverse(_p(uniq), _p(inverse), _p(n_unique), _p(data), n, _p(ws), ws_bytes, _stream()),
+          "sg_unique_inverse")
+    return uniq[:int(n_unique.item())], inverse
+
+
+def merge_nodes(node_ids_l):
+    """mxgraph.graph.merge_nodes for a list of int32 device tensors: (uniq_node_ids, [indices per input])."""
+    if isinstance(node_ids_l, torch.Tensor):
+        return unique_inverse(node_ids_l)
+    uniq, inv = unique_inverse(torch.cat([t.reshape(-1) for t in node_ids_l]))
+    out, begin = [], 0
+    for t in node_ids_l:
+        out.append(inv[begin:begin + t.numel()])
+        begin += t.numel()
+    return uniq, out
+
+
+__all__ = ["DeviceCSR", "unique_inverse", "merge_nodes"]

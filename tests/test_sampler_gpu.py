@@ -176,3 +176,53 @@ def test_value_outside_multi_link_is_reported():
     sampled, dst_indptr, n_sel = g.sample_positions(None, -1)
     with pytest.raises(ValueError):
         g.split(sampled, dst_indptr, n_sel, check_values=True)
+
+
+def test_remove_edges_bit_exact():
+    """Per-iteration batch-edge removal (graph_sampler.cpp:154-201) on the device."""
+    indptr, cols, vals, levels, rows = make_graph(10)
+    g, rd, cd = build(indptr, cols, vals, levels, 180, rows)
+    rs = np.random.RandomState(2)
+    pick = rs.choice(cols.size, 900, replace=False)
+    rm_r = np.concatenate([rows[pick], [5, 7, 299, 3]]).astype(np.int32)       # + pairs that do not exist / empty rows
+    rm_c = np.concatenate([cols[pick], [179, 0, 0, 1]]).astype(np.int32)
+    new = g.remove_edges(rm_r, rm_c)
+    if ref.available():
+        want_ep, want_val, want_ptr = ref.remove_edges(cols, vals, indptr, rm_r, rm_c)
+    else:
+        key = set(zip(rm_r.tolist(), rm_c.tolist()))
+        keep = np.array([(r, c) not in key for r, c in zip(rows.tolist(), cols.tolist())])
+        want_ep, want_val = cols[keep], vals[keep]
+        want_ptr = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=300))]).astype(np.int32)
+    assert np.array_equal(new.ind_ptr.cpu().numpy(), want_ptr)
+    assert np.array_equal(new.end_points.cpu().numpy(), want_ep)
+    assert np.array_equal(new.values.cpu().numpy(), want_val)
+    # support recomputed from the NEW degrees, bit-exact with get_support on the new matrix
+    nrd = np.diff(want_ptr).astype(np.int32)
+    ncd = np.bincount(want_ep, minlength=180).astype(np.int32)
+    if ref.available():
+        want_sup = ref.get_support(nrd, ncd, want_ptr, want_ep, True)
+        assert np.array_equal(new.support.cpu().numpy().view(np.int32), want_sup.view(np.int32))
+    # removing nothing is the identity
+    same = g.remove_edges(np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert torch.equal(same.ind_ptr, g.ind_ptr) and torch.equal(same.end_points, g.end_points)
+    assert torch.equal(same.support, g.support)
+
+
+@pytest.mark.parametrize("n,hi", [(1, 5), (50, 8), (5000, 300), (200000, 70000)])
+def test_unique_inverse_first_occurrence_order(n, hi):
+    """Plan construction primitive (graph_sampler.h:510-534, serial variant): bit-exact."""
+    from stargcn_b200.sampler import merge_nodes, unique_inverse
+    rs = np.random.RandomState(n)
+    data = rs.randint(0, hi, n).astype(np.int32)
+    uniq, inv = unique_inverse(torch.from_numpy(data).cuda())
+    _, first = np.unique(data, return_index=True)
+    want_uniq = data[np.sort(first)]                      # values in order of first appearance
+    lut = {int(v): k for k, v in enumerate(want_uniq)}
+    want_inv = np.array([lut[int(v)] for v in data], np.int32)
+    assert np.array_equal(uniq.cpu().numpy(), want_uniq)
+    assert np.array_equal(inv.cpu().numpy(), want_inv)
+    assert np.array_equal(uniq.cpu().numpy()[inv.cpu().numpy()], data)
+    a, b = torch.from_numpy(data[: n // 2]).cuda(), torch.from_numpy(data[n // 2:]).cuda()
+    u2, (ia, ib) = merge_nodes([a, b])
+    assert torch.equal(u2, uniq) and torch.equal(torch.cat([ia, ib]), inv)
