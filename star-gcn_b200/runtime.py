@@ -34,7 +34,9 @@ def fork_join(streams):
 class GraphedStep:
     """Capture ``fn()`` once, replay it on every call.  ``fn`` must launch fixed-shape work on the current
     stream (or on streams forked from it), must not synchronise with the host, and must keep using the
-    same input tensors (update them in place between replays)."""
+    same input tensors (update them in place between replays).  Nothing may keep the autograd graph of an
+    earlier eager call of ``fn`` alive (e.g. a retained non-detached output): its AccumulateGrad nodes would
+    be bound to another stream and break the capture."""
 
     def __init__(self, fn, warmup=3):
         self.fn = fn
