@@ -16,6 +16,8 @@
 // Reference kernels replaced: SegTakeKCorrBackwardEmbed1Kernel (seg_op.cu:682-722),
 // SegTakeKCorrBackwardEmbed2Kernel (seg_op.cu:747-790), SegPoolKernel sum/mean
 // (seg_op.cu:1057-1135), SegPoolBackwardKernel sum/mean (seg_op.cu:1171-1215).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -196,8 +198,13 @@ __device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *_
   else return 1.f / (float)(__ldg(a.inv_len_indptr + id + 1) - __ldg(a.inv_len_indptr + id));
 }
 
-template <int LPR, int UNROLL, int WMODE, bool WSUM>
+// LPR lanes x NV float4 per lane cover one row (F = LPR * NV * 4): lane l loads the float4 at column
+// (v * LPR + l) * 4, so each of the NV load instructions of a group touches LPR * 16 contiguous bytes.
+// NV = 2 at D = 64 puts FOUR work items in a warp instead of two: half the issued instructions per
+// edge, which is what bounds the short-segment (user-side) launch.
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM>
 __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs a) {
+  constexpr int F = LPR * NV * 4;
   const int lane = threadIdx.x & (LPR - 1);
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int n_groups = (gridDim.x * blockDim.x) / LPR;
@@ -207,78 +214,94 @@ __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs 
   const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
   float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
   const int32_t *__restrict__ idx = a.idx;
-  const int ld4 = a.ld_src >> 2;
+  constexpr int ld4 = F / 4;
   const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
 
   for (int it = group; it < n_items; it += n_groups) {
     int4 d;
     if (a.hdr) d = __ldg(a.items + it);
     else d = make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     float wacc = 0.f;
     int p = d.x;
     for (; p + UNROLL <= d.y; p += UNROLL) {
       int id[UNROLL];
       float wv[UNROLL];
-      float4 val[UNROLL];
+      float4 val[UNROLL][NV];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) id[u] = __ldg(idx + p + u);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) val[u] = __ldg(src + (long long)id[u] * ld4);
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) val[u][v] = __ldg(src + (long long)id[u] * ld4 + v * LPR);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) wv[u] = edge_weight<WMODE>(a, w, p + u, id[u]);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if constexpr (WSUM) wacc += wv[u];
-        acc.x = fmaf(wv[u], val[u].x, acc.x);
-        acc.y = fmaf(wv[u], val[u].y, acc.y);
-        acc.z = fmaf(wv[u], val[u].z, acc.z);
-        acc.w = fmaf(wv[u], val[u].w, acc.w);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          acc[v].x = fmaf(wv[u], val[u][v].x, acc[v].x);
+          acc[v].y = fmaf(wv[u], val[u][v].y, acc[v].y);
+          acc[v].z = fmaf(wv[u], val[u][v].z, acc[v].z);
+          acc[v].w = fmaf(wv[u], val[u][v].w, acc[v].w);
+        }
       }
     }
     if (p < d.y) {  // tail: one predicated batch
       int id[UNROLL];
       float wv[UNROLL];
-      float4 val[UNROLL];
+      float4 val[UNROLL][NV];
 #pragma unroll
       for (int u = 0; u < UNROLL - 1; ++u) id[u] = p + u < d.y ? __ldg(idx + p + u) : -1;
 #pragma unroll
       for (int u = 0; u < UNROLL - 1; ++u)
-        val[u] = id[u] >= 0 ? __ldg(src + (long long)id[u] * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          val[u][v] = id[u] >= 0 ? __ldg(src + (long long)id[u] * ld4 + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < UNROLL - 1; ++u) wv[u] = id[u] >= 0 ? edge_weight<WMODE>(a, w, p + u, id[u]) : 0.f;
 #pragma unroll
       for (int u = 0; u < UNROLL - 1; ++u) {
         if (id[u] >= 0) {  // keeps the addition order of the serial loop and never touches a masked row
           if constexpr (WSUM) wacc += wv[u];
-          acc.x = fmaf(wv[u], val[u].x, acc.x);
-          acc.y = fmaf(wv[u], val[u].y, acc.y);
-          acc.z = fmaf(wv[u], val[u].z, acc.z);
-          acc.w = fmaf(wv[u], val[u].w, acc.w);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(wv[u], val[u][v].x, acc[v].x);
+            acc[v].y = fmaf(wv[u], val[u][v].y, acc[v].y);
+            acc[v].z = fmaf(wv[u], val[u][v].z, acc[v].z);
+            acc[v].w = fmaf(wv[u], val[u][v].w, acc[v].w);
+          }
         }
       }
     }
 
     if (d.w >= 0) {  // piece of a split segment: park the partial row
-      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * (LPR * 4);
-      reinterpret_cast<float4 *>(prow)[lane] = acc;
+      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * F;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) reinterpret_cast<float4 *>(prow)[v * LPR + lane] = acc[v];
       if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
     } else {
       float *orow = out + out_offset(a, d.z);
-      if (a.mean && d.y > d.x) {
-        const float inv = 1.f / (float)(d.y - d.x);
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-      }
-      if (a.req == SG_REQ_ADD) {
-        const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
-        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-      }
-      if (a.out_lo) {
-        const float4 hi = make_float4(tf32_hi(acc.x), tf32_hi(acc.y), tf32_hi(acc.z), tf32_hi(acc.w));
-        reinterpret_cast<float4 *>(orow)[lane] = hi;
-        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
-      } else {
-        reinterpret_cast<float4 *>(orow)[lane] = acc;
+      const float inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float4 r = acc[v];
+        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+        if (a.req == SG_REQ_ADD) {
+          const float4 o = reinterpret_cast<const float4 *>(orow)[v * LPR + lane];
+          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        }
+        if (a.out_lo) {
+          const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
+          reinterpret_cast<float4 *>(orow)[v * LPR + lane] = hi;
+          reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[v * LPR + lane] =
+              make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
+        } else {
+          reinterpret_cast<float4 *>(orow)[v * LPR + lane] = r;
+        }
       }
       if (WSUM && lane == 0) store_wsum(a, d.z, wacc);
     }
@@ -389,34 +412,43 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int LPR, int WMODE, bool WSUM>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  constexpr int UNROLL = 8;
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_fast_kernel<LPR, UNROLL, WMODE, WSUM><<<grid, kThreads, 0, st>>>(a);
+  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM><<<grid, kThreads, 0, st>>>(a);
   SG_LAUNCHED("gather_rows_fast_kernel");
   if (a.hdr && n_long_cap > 0) {
     long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
     if (cb > cap) cb = cap;
     dim3 cgrid((unsigned)cb, (unsigned)K, 1);
-    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
+    combine_partials_kernel<4, LPR, NV><<<cgrid, kThreads, 0, st>>>(a);
     SG_LAUNCHED("combine_partials_kernel");
   }
   return SG_OK;
 }
 
-template <int LPR>
+template <int LPR, int NV, int UNROLL>
 static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  if (a.inv_len_indptr) return launch_fast<LPR, 3, false>(a, K, n_items_cap, n_long_cap, st);
-  if (!a.w) return launch_fast<LPR, 0, false>(a, K, n_items_cap, n_long_cap, st);
-  if (a.perm) return launch_fast<LPR, 2, false>(a, K, n_items_cap, n_long_cap, st);
-  if (a.wsum) return launch_fast<LPR, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return launch_fast<LPR, 1, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.inv_len_indptr) return launch_fast<LPR, NV, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
+  if (!a.w) return launch_fast<LPR, NV, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.perm) return launch_fast<LPR, NV, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.wsum) return launch_fast<LPR, NV, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
+  return launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
+}
+
+// Tuning knob (development only): SG_GATHER_SHAPE=0|1|2 picks the lane layout of the D=64 fast path.
+static int gather_shape() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SG_GATHER_SHAPE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
@@ -445,10 +477,13 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
                   a.partial_batch_stride % 2 == 0;
   if (v4 && a.ld_src == a.F && (!a.wsum || (a.w && !a.perm && !a.inv_len_indptr))) {  // exact-width fast path
     switch (a.F) {
-      case 16: return dispatch_fast_mode<4>(a, K, n_items_cap, n_long_cap, st);
-      case 32: return dispatch_fast_mode<8>(a, K, n_items_cap, n_long_cap, st);
-      case 64: return dispatch_fast_mode<16>(a, K, n_items_cap, n_long_cap, st);
-      case 128: return dispatch_fast_mode<32>(a, K, n_items_cap, n_long_cap, st);
+      case 16: return dispatch_fast_mode<4, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+      case 32: return dispatch_fast_mode<8, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+      case 64:
+        if (gather_shape() == 1) return dispatch_fast_mode<8, 2, 4>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 2) return dispatch_fast_mode<8, 2, 8>(a, K, n_items_cap, n_long_cap, st);
+        return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+      case 128: return dispatch_fast_mode<32, 1, 8>(a, K, n_items_cap, n_long_cap, st);
       default: break;
     }
   }

@@ -22,6 +22,8 @@
 // bits of the instruction descriptor.  Split-K partials are summed in a fixed order.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sg {
@@ -39,6 +41,8 @@ struct GemmArgs {
   int kb_total;      // number of BK-wide k-blocks
   int kb_per_split;
   int tiles_m, tiles_n, splits;
+  int chain_kb;      // k-blocks per TMEM accumulation chain (kChainKBlocks; tuning knob SG_GEMM_CHAIN)
+  int first_pass;    // 0 normally; 2 = issue only the hi.hi product (timing experiment SG_GEMM_PASSES=1, wrong numerics)
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
   const float *bias; // optional [N], added before the activation
@@ -133,12 +137,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 //
 // Accumulation accuracy: the tensor core adds into its fp32 TMEM accumulator with truncation
 // (measured: a 252-MMA chain at K=650 lands 3.5e-6 relative BELOW the exact magnitude, always
-// toward zero).  To stay an order of magnitude inside the 1e-5 parity bar at any K, a TMEM
-// accumulator only ever holds a chain of kChainKBlocks k-blocks (24 MMAs); the epilogue
-// warps drain it (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest
-// while the MMA warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).
+// toward zero).  To stay well inside the 1e-5 parity bar at any K, a TMEM accumulator only ever
+// holds a chain of kChainKBlocks k-blocks (96 MMAs, <= 1.5e-6); the epilogue warps drain it
+// (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest while the MMA
+// warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).  Shorter chains cost
+// time (the drain is exposed: chain 2 -> 8 takes the forward GEMM from 0.155 to 0.119 ms).
 // ---------------------------------------------------------------------------------------------
-constexpr int kChainKBlocks = 2;  // 2 k-blocks x 3 hi/lo products x 4 = 24 MMAs per TMEM chain
+constexpr int kChainKBlocks = 8;  // 8 k-blocks x 3 hi/lo products x 4 = 96 MMAs per TMEM chain
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
         for (int i = 0; i < n_kb; ++i, ++v) {
           const int s = v % STAGES;
           const uint32_t ph = (v / STAGES) & 1;
-          const int vin = i % kChainKBlocks;
+          const int vin = i % g.chain_kb;
           const int buf = chain & 1;
           if (vin == 0) {  // start of a chain: the epilogue warps must have drained this buffer
             mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
                          sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
+          for (int pass = g.first_pass; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
             const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -264,11 +269,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
                 da = make_smem_desc(sa + k * 32, 16, 1024, 2);
                 db = make_smem_desc(sb + k * 32, 16, 1024, 2);
               }
-              umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin | pass | k) != 0);
+              umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != g.first_pass) || (k != 0));
             }
           }
           umma_commit(&empty_bar[s]);
-          if (vin == kChainKBlocks - 1 || i == n_kb - 1) {
+          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
             umma_commit(&tmem_full_bar[buf]);
             ++chain;
           }
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
       const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
       const int m0 = (rem / tiles_n) * kBM, n0 = (rem % tiles_n) * BN;
       const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-      const int n_chains = (kb_end - kb_begin + kChainKBlocks - 1) / kChainKBlocks;
+      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
       const bool active = n0 + cbase < g.N;  // warp-uniform
       float racc[BN / 2];
 #pragma unroll
@@ -341,6 +346,244 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __gr
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster own one 256 x 256 output tile.
+// Each CTA loads ITS 128 rows of A and ITS half of the B tile (hi + lo: 64 KB per k-block instead of
+// 96 KB), the leader CTA issues M=256 MMAs that read both CTAs' shared memory and write both CTAs'
+// TMEM, and tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs.
+// Why: with fp32 operands pre-split into hi + lo the kernel streams 8 bytes per operand element, and the
+// B tile (the weights) is re-streamed from L2 by every M tile — the single-CTA kernel moves 1.1 GB
+// through the L2->SM fabric for the ML-10M forward transform and is bound by it, not by the tensor pipe
+// (issuing one of the three products instead of all three changes its time by 15 %).  A pair halves the
+// B traffic per SM (64 KB stages, 3-deep ring).  Measured: 0.647 -> 0.545 ms for the six GEMMs of a step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
+
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES, bool MN_MAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+    tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                            const GemmArgs g) {
+  constexpr int BN = 256;                  // tile columns (UMMA N); each CTA stores all BN columns of its 128 rows
+  constexpr int A_BYTES = kBM * kBK * 4;   // this CTA's 128 rows of A
+  constexpr int B_BYTES = 128 * kBK * 4;   // this CTA's half of the B tile
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int STG_FLOATS = 32 * 33;
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
+                                  ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(256 >> 4) << 24);  // M = 256 over the pair
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+  __shared__ uint64_t full_bar[STAGES];    // used on the leader only (both CTAs' TMA bytes land on it)
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];   // used on the leader only (both CTAs' epilogue warps arrive)
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;  // tiles_m counts 256-row pair tiles
+  const int n_tiles = tiles_mn * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int v = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const int nb0 = n0 + (int)rank * (n_eff >> 1);  // this CTA supplies B rows [nb0, nb0 + n_eff/2)
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // bytes of BOTH CTAs
+          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
+          if constexpr (MN_MAJOR) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              tma_load_2d_pair(sa_hi + a * (kBK * 128), &map_a_hi, &full_bar[s], m0 + a * 32, kb * kBK);
+              tma_load_2d_pair(sa_lo + a * (kBK * 128), &map_a_lo, &full_bar[s], m0 + a * 32, kb * kBK);
+              tma_load_2d_pair(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + a * 32, kb * kBK);
+              tma_load_2d_pair(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
+            }
+          } else {
+            tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
+            tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
+            tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
+            tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int v = 0, chain = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int n0 = (rem % tiles_n) * BN;
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        const int n_kb = kb_end - kb_begin;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        for (int i = 0; i < n_kb; ++i, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          const int vin = i % g.chain_kb;
+          const int buf = chain & 1;
+          if (vin == 0) {
+            mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
+                         sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+          for (int pass = g.first_pass; pass < 3; ++pass) {
+            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              uint64_t da, db;
+              if constexpr (MN_MAJOR) {
+                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
+                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
+              } else {
+                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+              }
+              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != g.first_pass) || (k != 0));
+            }
+          }
+          umma_commit_pair(&empty_bar[s]);
+          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
+            umma_commit_pair(&tmem_full_bar[buf]);
+            ++chain;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int cbase = h * (BN / 2);
+    float *stg = stg_all + (warp - 2) * STG_FLOATS;
+    int chain = 0;
+    for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+      const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
+      const bool active = n0 + cbase < g.N && m0 < g.M;  // warp-uniform
+      float racc[BN / 2];
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
+      for (int c = 0; c < n_chains; ++c, ++chain) {
+        const int buf = chain & 1;
+        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+        tc_fence_after();
+        if (active) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
+      }
+      if (active) {
+        float *dbase = g.D + (long long)z * g.split_stride;
+        const int row0 = m0 + q * 32;
+#pragma unroll
+        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+          const int col = n0 + cbase + ch * 32 + lane;
+          if (n0 + cbase + ch * 32 >= g.N) break;
+          float bias = 0.f;
+          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
+          __syncwarp();
+          const int rows = min(32, g.M - row0);
+          for (int rr = 0; rr < rows; ++rr) {
+            float x = stg[rr * 33 + lane] + bias;
+            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
+            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -461,6 +704,35 @@ static int launch_gemm(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cud
   return SG_OK;
 }
 
+template <int STAGES, bool MN>
+static int launch_gemm_pair(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel<STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  g.tiles_m = ceil_div(g.M, 256);
+  g.tiles_n = ceil_div(g.N, 256);
+  g.splits = splits;
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = (int)(n_tiles < max_pairs ? n_tiles : max_pairs);
+  tf32x3_gemm_pair_kernel<STAGES, MN><<<2 * pairs, kGemmThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  SG_LAUNCHED("tf32x3_gemm_pair_kernel");
+  return SG_OK;
+}
+
+// SG_GEMM_PAIR=0 selects the single-CTA kernel (A/B comparison); default: CTA pairs
+static bool use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SG_GEMM_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static inline int grid_ew(long long n) {
   long long gsz = ceil_div<long long>(n > 0 ? n : 1, 256);
   long long cap = (long long)num_sms() * 32;
@@ -493,6 +765,13 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
   SG_REQUIRE(splits == 1 || (split_ws && epilogue == 0 && !bias), "sg_gemm_tf32x3: split-K needs a workspace and the plain epilogue");
   GemmArgs g;
   g.M = M; g.N = N; g.epi = epilogue; g.slope = slope; g.bias = bias;
+  {
+    static int chain = -1, passes = -1;
+    if (chain < 0) { const char *e = getenv("SG_GEMM_CHAIN"); chain = e ? atoi(e) : kChainKBlocks; if (chain < 1) chain = 1; }
+    if (passes < 0) { const char *e = getenv("SG_GEMM_PASSES"); passes = e ? atoi(e) : 3; }
+    g.chain_kb = chain;
+    g.first_pass = passes == 1 ? 2 : 0;
+  }
   g.kb_total = ceil_div(K, kBK);
   g.kb_per_split = ceil_div(g.kb_total, splits);
   splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split
@@ -507,13 +786,18 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
     if ((rc = make_map_mnmajor(&maps[1], A_lo, K, M, lda)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[3], B_lo, K, N, ldb)) != SG_OK) return rc;
-    if ((rc = launch_gemm<256, 2, true>(maps, g, splits, st)) != SG_OK) return rc;
+    if (use_pair()) rc = launch_gemm_pair<3, true>(maps, g, splits, st);
+    else rc = launch_gemm<256, 2, true>(maps, g, splits, st);
+    if (rc != SG_OK) return rc;
   } else {
+    const int b_rows = use_pair() ? 128 : BN;  // a CTA of a pair loads half of the B tile
     if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
     if ((rc = make_map_kmajor(&maps[1], A_lo, M, K, lda, kBM)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, BN)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[3], B_lo, N, K, ldb, BN)) != SG_OK) return rc;
-    if ((rc = launch_gemm<256, 2, false>(maps, g, splits, st)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, b_rows)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[3], B_lo, N, K, ldb, b_rows)) != SG_OK) return rc;
+    if (use_pair()) rc = launch_gemm_pair<3, false>(maps, g, splits, st);
+    else rc = launch_gemm<256, 2, false>(maps, g, splits, st);
+    if (rc != SG_OK) return rc;
   }
   if (splits > 1) {
     splitk_reduce_kernel<<<grid_ew((long long)M * N), 256, 0, st>>>(D, ldd, split_ws, M, N, splits);

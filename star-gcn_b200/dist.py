@@ -13,7 +13,11 @@ SURVEY §2.2).  This module is the B200-native answer for one box of 8 GPUs (SUR
     concatenated table ``[local rows ; halo rows]`` through column ids rewritten once per plan
   * backward is the transpose: halo-slot gradients go back through the reverse all-to-all and
     are summed into the owner's rows in a fixed order (sorted gather, no atomics)
-  * the small relation-weight gradients are all-reduced (``allreduce_grads``)
+  * when the halo is dense (at least half of all remote rows are needed by every rank — the case for a
+    rating graph without locality) the exchange degenerates to an all-gather of the equal-sized blocks and
+    its transpose to a reduce-scatter: ``HaloPlan(mode="auto")`` then uses those NVSwitch collectives
+    directly, with no pack / unpack and the global ids as column ids
+  * the small relation-weight gradients are all-reduced (inside the fused backward, or ``allreduce_grads``)
 
 Index bookkeeping (``HaloPlan``) is host-side numpy + one all-to-all of index lists per plan and
 runs under gloo on CPU tensors as well (tests/test_dist_cpu.py); the row traffic itself needs
@@ -69,15 +73,35 @@ class HaloPlan:
     torch.distributed on ``index_device`` (cuda for NCCL, cpu for gloo).
     """
 
-    def __init__(self, cols_global, owner_ranges, rank, world, group=None, index_device="cpu", exchange_fn=None):
+    def __init__(self, cols_global, owner_ranges, rank, world, group=None, index_device="cpu", exchange_fn=None,
+                 mode="auto"):
         cols = np.asarray(cols_global, dtype=np.int64)
         self.rank, self.world = int(rank), int(world)
         self.owner_ranges = np.asarray(owner_ranges, dtype=np.int64)
         lo, hi = self.owner_ranges[rank], self.owner_ranges[rank + 1]
         self.n_local = int(hi - lo)
+        self.group = group
+        self._dev = None
         owner = np.searchsorted(self.owner_ranges, cols, side="right") - 1
         if cols.size and (cols.min() < 0 or cols.max() >= self.owner_ranges[-1]):
             raise ValueError("column id outside the partitioned id space")
+        if mode not in ("auto", "alltoall", "allgather"):
+            raise ValueError("mode must be 'auto', 'alltoall' or 'allgather'")
+        self.mode = self._choose_mode(mode, cols, owner, index_device, exchange_fn)
+        if self.mode == "allgather":
+            # dense halo: every rank fetches (almost) every remote row, so the exchange is an all-gather of the
+            # equal-sized blocks and its transpose a reduce-scatter (NVSwitch collectives, no pack / unpack);
+            # the concatenated table is indexed by the global ids themselves
+            self.local_cols = cols.astype(np.int32)
+            self.n_ext = int(self.owner_ranges[-1])
+            self.n_halo = self.n_ext - self.n_local
+            self.recv_ids = [np.arange(self.owner_ranges[q], self.owner_ranges[q + 1]) if q != rank else np.zeros(0, np.int64)
+                             for q in range(self.world)]
+            self.recv_counts = [int(r.size) for r in self.recv_ids]
+            self.send_idx = [np.arange(self.n_local, dtype=np.int32) if q != rank else np.zeros(0, np.int32)
+                             for q in range(self.world)]
+            self.send_counts = [int(s_.size) for s_ in self.send_idx]
+            return
         self.recv_ids, local_cols = [], np.empty(cols.shape, np.int64)
         mine = owner == rank
         local_cols[mine] = cols[mine] - lo
@@ -108,8 +132,27 @@ class HaloPlan:
         for q, s in enumerate(self.send_idx):
             if s.size and (s.min() < 0 or s.max() >= self.n_local):
                 raise ValueError(f"rank {q} requested a row this rank does not own")
-        self.group = group
-        self._dev = None
+
+    def _choose_mode(self, mode, cols, owner, index_device, exchange_fn):
+        """'allgather' needs equal blocks; 'auto' picks it when at least half of all remote rows are needed by
+        EVERY rank (decided collectively so that all ranks take the same path)."""
+        sizes = np.diff(self.owner_ranges)
+        equal = bool(np.all(sizes == sizes[0]))
+        if self.world == 1 or mode == "alltoall":
+            return "alltoall"
+        if mode == "allgather":
+            if not equal:
+                raise ValueError("allgather mode needs equal-sized ownership blocks")
+            return "allgather"
+        remote = owner != self.rank
+        n_needed = np.unique(cols[remote]).size
+        n_remote = int(self.owner_ranges[-1]) - self.n_local
+        want = int(equal and n_remote > 0 and n_needed >= 0.5 * n_remote)
+        if exchange_fn is not None or not dist.is_initialized():
+            return "allgather" if want else "alltoall"
+        flag = torch.tensor([want], dtype=torch.int32, device=torch.device(index_device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return "allgather" if int(flag.item()) else "alltoall"
 
     # ---- device-side state for the row exchange ----
     def to(self, device):
@@ -144,6 +187,26 @@ def _a2a_rows(out, inp, out_splits, in_splits, group):
         out.copy_(host)
 
 
+def _all_gather_rows(out, inp, group):
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, inp, group=group)
+    else:  # gloo test transport
+        world = dist.get_world_size(group)
+        parts = [torch.empty(inp.shape, dtype=inp.dtype) for _ in range(world)]
+        dist.all_gather(parts, inp.cpu(), group=group)
+        out.copy_(torch.cat(parts))
+
+
+def _reduce_scatter_rows(out, inp, group):
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, inp, group=group)
+    else:  # gloo test transport
+        host = inp.cpu()
+        dist.all_reduce(host, group=group)
+        r, n = dist.get_rank(group), out.shape[0]
+        out.copy_(host[r * n:(r + 1) * n])
+
+
 class _HaloExchange(torch.autograd.Function):
     """x_local [n_local, D] -> x_ext [n_local + n_halo, D] (local rows, then halo rows by owner, by id)."""
 
@@ -152,6 +215,10 @@ class _HaloExchange(torch.autograd.Function):
         d = plan._dev
         D = x_local.shape[1]
         x_ext = torch.empty((plan.n_ext, D), dtype=torch.float32, device=x_local.device)
+        ctx.plan, ctx.D = plan, D
+        if plan.mode == "allgather":
+            _all_gather_rows(x_ext, x_local, plan.group)
+            return x_ext
         x_ext[:plan.n_local].copy_(x_local)
         if plan.world > 1:
             if d["send_cat"].numel():   # pack: one gather launch over the cached one-edge-per-slot pattern
@@ -159,12 +226,15 @@ class _HaloExchange(torch.autograd.Function):
             else:
                 send = torch.empty((0, D), dtype=torch.float32, device=x_local.device)
             _a2a_rows(x_ext[plan.n_local:], send, plan.recv_counts, plan.send_counts, plan.group)
-        ctx.plan, ctx.D = plan, D
         return x_ext
 
     @staticmethod
     def backward(ctx, g_ext):
         plan, D = ctx.plan, ctx.D
+        if plan.mode == "allgather":
+            g_local = torch.empty((plan.n_local, D), dtype=torch.float32, device=g_ext.device)
+            _reduce_scatter_rows(g_local, g_ext.contiguous(), plan.group)
+            return g_local, None
         g_local = g_ext[:plan.n_local].clone()
         if plan.world > 1:
             n_send = sum(plan.send_counts)

@@ -38,7 +38,10 @@ def _worker(rank, world, port, q):
         res = {}
         for side, ranges, xg in (("user", part["item_ranges"], x_item_global), ("item", part["user_ranges"], x_user_global)):
             indptr, cols, vals, sup = part[side]
-            plan = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu")
+            plan = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="alltoall")
+            # dense halo -> the collectively chosen mode is the all-gather one: global ids index the gathered table
+            auto = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="auto")
+            ok_auto = auto.mode == "allgather" and auto.n_ext == xg.shape[0] and np.array_equal(auto.local_cols, cols)
             lo, hi = ranges[rank], ranges[rank + 1]
             x_local = torch.from_numpy(xg[lo:hi])
             # row exchange emulated with a gloo all-to-all on CPU tensors (test stand-in for pack kernel + NCCL)
@@ -49,7 +52,7 @@ def _worker(rank, world, port, q):
             x_ext = torch.cat([x_local, halo]).numpy()
             ok_rows = np.array_equal(x_ext[plan.local_cols], xg[cols])          # rewritten ids address the right rows
             ok_sorted = all(np.all(np.diff(r) > 0) for r in plan.recv_ids if r.size > 1)
-            res[side] = dict(ok_rows=bool(ok_rows), ok_sorted=bool(ok_sorted), n_halo=plan.n_halo, n_local=plan.n_local,
+            res[side] = dict(ok_rows=bool(ok_rows and ok_auto), ok_sorted=bool(ok_sorted), n_halo=plan.n_halo, n_local=plan.n_local,
                              send_counts=plan.send_counts, recv_counts=plan.recv_counts, nnz=int(cols.size),
                              edges=set(zip(np.repeat(np.arange(len(indptr) - 1) + (part["user_ranges"] if side == "user" else part["item_ranges"])[rank],
                                                      np.diff(indptr)).tolist(), cols.tolist())))

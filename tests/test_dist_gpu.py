@@ -56,7 +56,7 @@ def _make_agg(ws, bs):
     return agg
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -66,7 +66,8 @@ def _worker(rank, world, port, q):
         base = _base()
         part = sgd.partitioned_layer_inputs(base, rank, world)
         indptr, cols, vals, sup = part["user"]
-        plan = sgd.HaloPlan(cols, part["item_ranges"], rank, world, index_device="cpu")
+        plan = sgd.HaloPlan(cols, part["item_ranges"], rank, world, index_device="cpu", mode=mode)
+        assert plan.mode == mode
         ep_l, ptr_l, sup_l, _ = synth.split_by_level(indptr, plan.local_cols, vals, sup, base["levels"])
         csr = MultiLinkCSR(ep_l, ptr_l, sup_l, n_nb=plan.n_ext, device="cuda")
         x_item, gout = _globals(world, base)
@@ -84,12 +85,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(600)
-def test_partitioned_layer_matches_whole_graph():
+@pytest.mark.parametrize("mode", ["alltoall", "allgather"])
+def test_partitioned_layer_matches_whole_graph(mode):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=400) for _ in range(world))
