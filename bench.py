@@ -289,7 +289,10 @@ def run_gpu_arm(args, rank, world, local_rank):
         rng = np.random.default_rng(2000 + rank)
         for side, nb_ranges, n_dst in (("user", part["item_ranges"], wl["n_user"]), ("item", part["user_ranges"], wl["n_item"])):
             indptr, cols, vals, sup = part[side]
-            plan = sgd.HaloPlan(cols, nb_ranges, rank, world, index_device=dev).to(dev)
+            # one communicator per direction: their collectives then run on independent NCCL streams and one
+            # direction's exchange overlaps the other direction's compute instead of queueing behind it
+            side_group = dist.new_group(backend="nccl")
+            plan = sgd.HaloPlan(cols, nb_ranges, rank, world, group=side_group, index_device=dev).to(dev)
             lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, wl["base"]["levels"])[:3]
             csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev).prepare(backward=True)
             x_np = rng.standard_normal((plan.n_local, D), dtype=np.float32)
@@ -302,7 +305,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                 getattr(agg, f"weight{i}").copy_(torch.from_numpy(ws[i]))
                 getattr(agg, f"bias{i}").copy_(torch.from_numpy(bs[i]))
         if world > 1:
-            agg.grad_group = dist.group.WORLD     # weight-gradient all-reduce inside the fused backward
+            agg.grad_group = s_["plan"].group     # weight-gradient all-reduce inside the fused backward
         s_["agg"] = agg
         s_["x"] = torch.from_numpy(s_["x_np"]).to(dev).requires_grad_(True)
         s_["gout"] = torch.randn((s_["n_dst"], U), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
@@ -318,20 +321,30 @@ def run_gpu_arm(args, rank, world, local_rank):
     from stargcn_b200 import runtime
     side_streams = [torch.cuda.Stream(device=dev) for _ in sides]
 
-    def one_side(s):
+    def side_forward(s):
         s["x"].grad = None
         for p in s["agg"].parameters():
             p.grad = None
         xin = s["x"] if s["plan"] is None else sgd.halo_exchange(s["x"], s["plan"])
-        out = s["agg"](xin, s["csr"])
+        s["out"] = s["agg"](xin, s["csr"])
+
+    def side_backward(s):
+        out = s.pop("out")
         out.backward(s["gout"])
+
+    def one_side(s):
+        side_forward(s)
+        side_backward(s)
 
     def eager_step():
         # the two directions are independent: each on its own stream, so one direction's halo exchange /
-        # tensor-core GEMMs overlap the other's gathers
+        # tensor-core GEMMs overlap the other's gathers; both forwards are issued before both backwards so
+        # that neither direction's first collective queues behind the other's last one
         with runtime.fork_join(side_streams) as run:
             for i, s in enumerate(sides.values()):
-                run(i, lambda s=s: one_side(s))
+                run(i, lambda s=s: side_forward(s))
+            for i, s in enumerate(sides.values()):
+                run(i, lambda s=s: side_backward(s))
 
     step, graphed, launches_per_step = eager_step, False, None
     if not args.no_graph:

@@ -31,6 +31,17 @@ def _csr(rows, cols, vals, n_rows, n_cols):
     return indptr.astype(np.int32), cols.astype(np.int32), vals.astype(np.float32), rows.astype(np.int32)
 
 
+def _sorted_unique(x):
+    """np.unique for int64 keys via sort + neighbour compare (numpy 2.3's hash-based unique is ~8x slower here)."""
+    x = np.sort(x)
+    if x.size == 0:
+        return x
+    keep = np.empty(x.size, bool)
+    keep[0] = True
+    np.not_equal(x[1:], x[:-1], out=keep[1:])
+    return x[keep]
+
+
 def make_bipartite(n_user, n_item, n_edges, n_levels=10, seed=1000, alpha=1.0, c=20.0, sigma=1.0):
     """Returns a dict with both CSR directions ('u2i' rows=users, 'i2u' rows=items): indptr, cols,
     vals (rating level value), support, plus degrees and the level values."""
@@ -40,16 +51,18 @@ def make_bipartite(n_user, n_item, n_edges, n_levels=10, seed=1000, alpha=1.0, c
     p_item = rng.permutation(p_item / p_item.sum())
     p_user = rng.lognormal(0.0, sigma, n_user)
     p_user /= p_user.sum()
+    cdf_user, cdf_item = np.cumsum(p_user), np.cumsum(p_item)
     keys = np.zeros(0, np.int64)
     # every node gets one guaranteed edge; the rest are drawn from the two marginals and de-duplicated
     base = np.concatenate([np.arange(n_user, dtype=np.int64) * n_item + rng.integers(0, n_item, n_user),
                            rng.integers(0, n_user, n_item).astype(np.int64) * n_item + np.arange(n_item)])
-    keys = np.unique(base)
+    keys = _sorted_unique(base)
     while keys.size < n_edges:
         need = int((n_edges - keys.size) * 1.3) + 1024
-        u = rng.choice(n_user, size=need, p=p_user).astype(np.int64)
-        i = rng.choice(n_item, size=need, p=p_item).astype(np.int64)
-        keys = np.unique(np.concatenate([keys, u * n_item + i]))
+        # inverse-CDF sampling (searchsorted) — the same distribution as rng.choice(p=...) at a tenth of the time
+        u = np.minimum(np.searchsorted(cdf_user, rng.random(need), side="right"), n_user - 1).astype(np.int64)
+        i = np.minimum(np.searchsorted(cdf_item, rng.random(need), side="right"), n_item - 1).astype(np.int64)
+        keys = _sorted_unique(np.concatenate([keys, u * n_item + i]))
     if keys.size > n_edges:  # drop extras, never the guaranteed ones
         extra = np.setdiff1d(keys, base, assume_unique=True)
         drop = rng.choice(extra.size, size=keys.size - n_edges, replace=False)
@@ -57,7 +70,7 @@ def make_bipartite(n_user, n_item, n_edges, n_levels=10, seed=1000, alpha=1.0, c
     u, i = (keys // n_item).astype(np.int64), (keys % n_item).astype(np.int64)
     levels = (np.arange(n_levels) + 1).astype(np.float32) * (0.5 if n_levels == 10 else 1.0)
     p_lvl = LEVEL_P10 if n_levels == 10 else (LEVEL_P5 if n_levels == 5 else np.full(n_levels, 1.0 / n_levels))
-    vals = levels[rng.choice(n_levels, size=keys.size, p=p_lvl / p_lvl.sum())]
+    vals = levels[np.minimum(np.searchsorted(np.cumsum(p_lvl / p_lvl.sum()), rng.random(keys.size), side="right"), n_levels - 1)]
     deg_u = np.bincount(u, minlength=n_user).astype(np.int32)
     deg_i = np.bincount(i, minlength=n_item).astype(np.int32)
     out = dict(n_user=n_user, n_item=n_item, nnz=int(keys.size), levels=levels, deg_user=deg_u, deg_item=deg_i)
