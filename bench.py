@@ -319,7 +319,11 @@ def run_gpu_arm(args, rank, world, local_rank):
         total_edges = int(t.item())
 
     from stargcn_b200 import runtime
-    side_streams = [torch.cuda.Stream(device=dev) for _ in sides]
+    # the direction with the larger halo gets the higher stream priority: its (shorter) compute chain then
+    # finishes first and its big reduce-scatter overlaps the other direction's remaining compute
+    halo = [(s_["plan"].n_halo if s_["plan"] is not None else 0) for s_ in sides.values()]
+    side_streams = [torch.cuda.Stream(device=dev, priority=(-1 if world > 1 and h == max(halo) and h > 0 else 0))
+                    for h in halo]
 
     def side_forward(s):
         s["x"].grad = None
