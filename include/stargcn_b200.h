@@ -286,6 +286,23 @@ size_t sg_unique_inverse_ws_bytes(int n);
 int sg_unique_inverse(int32_t *uniq, int32_t *inverse, int32_t *n_unique, const int32_t *data, int n, void *ws,
                       size_t ws_bytes, sg_stream_t stream);
 
+/* Next rows  multi-tensor global-norm clip + Adam step, one launch over all parameters.
+ * replaces params_clip_global_norm (mxgraph/utils.py:104-107 -> gluon.utils.clip_global_norm) and
+ * gluon.Trainer('adam').step (experiments/STAR-GCN.py:552-553,630-632 -> mx adam_update).
+ * Tensors are addressed through DEVICE arrays of device pointers; `work` is a device array of
+ * (tensor index, chunk index) int32 pairs, one per sg_optim_chunk() elements of every tensor.
+ *   out2[0] = sqrt(sum ||g||^2),  out2[1] = min(1, max_norm / (norm + 1e-8));  ws: n_work floats */
+int sg_optim_chunk(void);
+int sg_global_norm(float *out2, const float *const *grads, const long long *numels, const void *work, int n_work,
+                   float max_norm, float *ws, sg_stream_t stream);
+/* g = g * clip_out2[1] (written back when write_back_grad) ; g = g * rescale + wd * w ;
+ * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; w -= lr_t * m / (sqrt(v) + eps)
+ * lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is computed by the caller; clip_out2 may be NULL. */
+int sg_multi_adam(float *const *params, float *const *grads, float *const *ms, float *const *vs,
+                  const long long *numels, const void *work, int n_work, float lr_t, float beta1, float beta2,
+                  float eps, float wd, float rescale, const float *clip_out2, int write_back_grad,
+                  sg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,8 +7,12 @@ the one-file shim ``stargcn_b200.py`` at the repo root.
     layers     mirror of ``mxgraph.layers`` (aggregators, HeterGCNLayer, StackedHeterGCNLayers)
     graph      device-resident multi-relation CSR plans + the fused aggregation op
     decoder    masked-embedding lookup, reconstruction decoder and losses
+    sampler    device-resident graph: neighbour sampling, level split, support, edge removal, id merging
+    dist       node-partitioned multi-GPU aggregation (halo exchange over NCCL)
+    runtime    CUDA-graph step capture and stream fork/join
+    optim      multi-tensor global-norm clip + Adam
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from . import seg_op, graph, layers, decoder, sampler, runtime  # noqa: F401
+from . import seg_op, graph, layers, decoder, sampler, runtime, optim  # noqa: F401
 
 __version__ = "0.1.0"

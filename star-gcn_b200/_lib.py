@@ -56,6 +56,9 @@ SIGNATURES = {
     "sg_bincount": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_p]),
     "sg_unique_inverse_ws_bytes": (_c_sz, [_c_int]),
     "sg_unique_inverse": (_c_int, [_c_p] * 4 + [_c_int, _c_p, _c_sz, _c_p]),
+    "sg_optim_chunk": (_c_int, []),
+    "sg_global_norm": (_c_int, [_c_p] * 4 + [_c_int, ctypes.c_float, _c_p, _c_p]),
+    "sg_multi_adam": (_c_int, [_c_p] * 6 + [_c_int] + [ctypes.c_float] * 6 + [_c_p, _c_int, _c_p]),
     "sg_masked_embed_fwd": (_c_int, [_c_p] * 5 + [_c_int] * 3 + [_c_p]),
     "sg_reduce_ws_bytes": (_c_sz, []),
     "sg_sq_err_fwd": (_c_int, [_c_p, _c_p, _c_p, ctypes.c_longlong, ctypes.c_float, _c_p, _c_p]),
