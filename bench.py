@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--sampled", type=int, default=0, metavar="K",
+                    help="N=1 only: build the layer inputs with the DEVICE sampler at fan-out K (0 = full neighbourhood lists)")
     return ap.parse_args()
 
 
@@ -277,7 +279,26 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- device-resident state: inputs live in HBM before the timed region starts ----
     sides = {}
-    if world == 1:
+    sampler_info = None
+    if world == 1 and args.sampled > 0:
+        # the whole graph resident on the device; neighbourhoods of every node sampled there (fan-out K)
+        from stargcn_b200.sampler import DeviceCSR
+        base = wl["base"]
+        sampler_info = dict(fanout=args.sampled)
+        for side, key, x_nb, n_dst, n_cols in (("user", "u2i", wl["x_item"], wl["n_user"], wl["n_item"]),
+                                               ("item", "i2u", wl["x_user"], wl["n_item"], wl["n_user"])):
+            c = base[key]
+            g_dev = DeviceCSR(c["indptr"], c["cols"], c["vals"], base["levels"], n_cols, support=c["support"], device=dev)
+            g_dev.sample_neighbors(None, args.sampled, seed=1)        # warm-up
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            csr = g_dev.sample_neighbors(None, args.sampled, seed=2)
+            ev1.record()
+            torch.cuda.synchronize()
+            sampler_info[side] = dict(ms=ev0.elapsed_time(ev1), sampled_edges=csr.nnz, graph_edges=g_dev.nnz)
+            sides[side] = dict(csr=csr.prepare(backward=True), x_np=x_nb, n_dst=n_dst, plan=None)
+    elif world == 1:
         for side, x_nb, n_dst in (("user", wl["x_item"], wl["n_user"]), ("item", wl["x_user"], wl["n_item"])):
             csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
             sides[side] = dict(csr=csr, x_np=x_nb, n_dst=n_dst, plan=None)
@@ -478,6 +499,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                   clocks=clocks, gpu_launches=int(launches), roofline=roofline)
     if transform is not None:
         result["transform_gemm"] = transform
+    if sampler_info is not None:
+        result["config"]["workload"] += f"; neighbourhoods sampled ON THE DEVICE at fan-out {args.sampled}"
+        result["device_sampler"] = sampler_info
     if e2e is not None:
         result["e2e"] = e2e
     return result, wl

@@ -173,3 +173,39 @@ def test_ml100k_shape_layer_vs_oracle():
         assert rel_err(host(xd.grad), gx_ref) <= TOL
         assert rel_err(host(agg.weight3.grad), gw_ref[3]) <= TOL
         assert rel_err(host(agg.bias3.grad), gb_ref[3]) <= TOL
+
+
+@pytest.mark.parametrize("case", ["no_edges", "no_dst_rows", "one_row"])
+def test_fused_aggregator_degenerate_shapes(case):
+    """Empty relations arrive as length-1 dummies with all-zero indptr (graph.py:221-222); a plan may also
+    select no destination node at all.  Forward and backward must still be well defined."""
+    from stargcn_b200.graph import MultiLinkCSR
+    R, D, U = 5, 64, 250
+    rs = np.random.RandomState(0)
+    ws = [rs.uniform(-0.3, 0.3, (U, D)).astype(np.float32) for _ in range(R)]
+    bs = [rs.uniform(-0.3, 0.3, (U,)).astype(np.float32) for _ in range(R)]
+    n_nb = 30
+    n_dst = {"no_edges": 17, "no_dst_rows": 0, "one_row": 1}[case]
+    if case == "one_row":
+        ep_l = [np.array([3, 7], np.int32)] + [np.zeros(1, np.int32)] * (R - 1)
+        ptr_l = [np.array([0, 2], np.int32)] + [np.zeros(2, np.int32)] * (R - 1)
+        sup_l = [np.array([0.5, 0.25], np.float32)] + [np.zeros(1, np.float32)] * (R - 1)
+    else:
+        ep_l = [np.zeros(1, np.int32)] * R
+        ptr_l = [np.zeros(n_dst + 1, np.int32)] * R
+        sup_l = [np.zeros(1, np.float32)] * R
+    agg = build_agg(ws, bs, R, U, "sum", "leaky", False)
+    x = rs.normal(size=(n_nb, D)).astype(np.float32)
+    xd = dev(x).requires_grad_(True)
+    out = agg(xd, MultiLinkCSR(ep_l, ptr_l, sup_l, n_nb, device="cuda"))
+    assert out.shape == (n_dst, U)
+    ref_out, pre = orl.multilink_aggregator_forward(x, ws, bs, ep_l, ptr_l, sup_l, "sum", "leaky")
+    if n_dst:
+        assert rel_err(host(out), ref_out) <= TOL or np.abs(ref_out).max() == 0
+        if np.abs(ref_out).max() == 0:
+            assert float(out.abs().max()) == 0.0            # no edges: exactly zero (bias * zero support sum)
+    out.backward(torch.ones_like(out))
+    assert xd.grad.shape == (n_nb, D) and torch.isfinite(xd.grad).all()
+    if case != "one_row":
+        assert float(xd.grad.abs().max()) == 0.0
+    assert all(torch.isfinite(getattr(agg, f"weight{i}").grad).all() for i in range(R))
