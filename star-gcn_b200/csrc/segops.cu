@@ -397,7 +397,11 @@ static int multilink_agg_fwd_impl(float *agg, float *agg_lo, int ld_agg, float *
   GatherArgs a;
   a.out = agg; a.out_lo = agg_lo; a.ld_out = ld_agg; a.n_out_rows = n_dst;
   a.src = x; a.ld_src = D;
-  a.w = support; a.idx = end_points; a.indptr = cat_indptr; a.F = D; a.req = SG_REQ_WRITE;
+  // with no edges at all the (empty) support / end-point arrays may be null; they are never read, but the
+  // kernel variant is chosen by pointer, so keep the weighted variant selected
+  a.w = support ? support : reinterpret_cast<const float *>(cat_indptr);
+  a.idx = end_points ? end_points : cat_indptr;
+  a.indptr = cat_indptr; a.F = D; a.req = SG_REQ_WRITE;
   a.wsum = wsum; a.wsum_lo = wsum_lo; a.wsum_ld = wsum_ld;
   a.plan_chunk = plan_chunk;
   if (plan) {
