@@ -11,8 +11,9 @@ the one-file shim ``stargcn_b200.py`` at the repo root.
     dist       node-partitioned multi-GPU aggregation (halo exchange over NCCL)
     runtime    CUDA-graph step capture and stream fork/join
     optim      multi-tensor global-norm clip + Adam
+    model      the encoder-decoder stack of experiments/STAR-GCN.py:Net assembled from the pieces above
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from . import seg_op, graph, layers, decoder, sampler, runtime, optim  # noqa: F401
+from . import seg_op, graph, layers, decoder, sampler, runtime, optim, model  # noqa: F401
 
 __version__ = "0.1.0"

@@ -36,3 +36,29 @@ def merge_nodes(node_ids):
 
 
 __all__ = ["unordered_unique", "merge_nodes"]
+
+
+def merge_node_ids_dict(dicts):
+    """Several ``{node_type: ids}`` requests -> (``{node_type: distinct ids in first-appearance order}``,
+    one ``{node_type: index into those}`` per request) — what mxgraph.graph.merge_node_ids_dict
+    (graph.py:166-219) returns for plain (non-edge) requests.  Requests are scanned in order, so the ids of
+    an earlier request come first in the merged list."""
+    per_type = {}
+    for d in dicts:
+        for key, ids in d.items():
+            per_type.setdefault(key, []).append(np.asarray(ids).reshape(-1))
+    merged, inverse = {}, {}
+    for key, arrays in per_type.items():
+        merged[key], inverse[key] = merge_nodes(arrays)
+    cursor = {key: 0 for key in per_type}
+    out = []
+    for d in dicts:
+        idx = {}
+        for key in d:
+            idx[key] = inverse[key][cursor[key]]
+            cursor[key] += 1
+        out.append(idx)
+    return merged, out
+
+
+__all__ += ["merge_node_ids_dict"]

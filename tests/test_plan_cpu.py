@@ -18,38 +18,7 @@ def test_unordered_unique_first_appearance_order():
     assert e.size == 0 and ei.size == 0
 
 
-class _HostCSR:
-    """Minimal stand-in for mxgraph.graph.CSRMat.sample_neighbors (full neighbourhood, ids = indices + offset)."""
-
-    def __init__(self, indptr, cols, vals, levels, row_ids, col_ids):
-        self.indptr, self.cols, self.vals, self.levels = indptr, cols, vals, levels
-        self.row_ids, self.col_ids = row_ids, col_ids
-        self._row_of = {int(r): k for k, r in enumerate(row_ids)}
-
-    def sample_neighbors(self, src_ids=None, symm=True, use_multi_link=True, num_neighbors=None):
-        rows = [self._row_of[int(i)] for i in src_ids]
-        pos = np.concatenate([np.arange(self.indptr[r], self.indptr[r + 1]) for r in rows] + [np.zeros(0, np.int64)]).astype(np.int64)
-        ptr = np.concatenate([[0], np.cumsum([self.indptr[r + 1] - self.indptr[r] for r in rows])]).astype(np.int32)
-        ep_ids, vals = self.col_ids[self.cols[pos]], self.vals[pos]
-        sup = np.full(pos.size, 0.5, np.float32)
-        if not use_multi_link:
-            return ep_ids, vals, ptr, sup
-        seg = np.repeat(np.arange(len(rows)), np.diff(ptr))
-        ep_l, val_l, ptr_l, sup_l = [], [], [], []
-        for lv in self.levels:
-            m = vals == lv
-            ep_l.append(ep_ids[m]); val_l.append(vals[m]); sup_l.append(sup[m])
-            ptr_l.append(np.concatenate([[0], np.cumsum(np.bincount(seg[m], minlength=len(rows)))]).astype(np.int32))
-        return ep_l, val_l, ptr_l, sup_l
-
-
-class _HostGraph:
-    def __init__(self, mats):
-        self._mats = mats
-        self.meta_graph = {"user": {"item": "rating"}, "item": {"user": "rev_rating"}}
-
-    def __getitem__(self, key):
-        return self._mats[key]
+from hostgraph import HostCSR as _HostCSR, HostGraph as _HostGraph  # noqa: E402
 
 
 def _graph(seed=0, n_user=12, n_item=9, nnz=40, R=3):

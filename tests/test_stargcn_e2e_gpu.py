@@ -1,0 +1,153 @@
+"""BASELINE.json config[1]: ML-100k-shaped transductive full STAR-GCN — two stacked encoder blocks, masked
+input embeddings, reconstruction decoder and rating head, D=64 — assembled by stargcn_b200.model.StarGCN,
+against a torch-CPU fp64 execution of the SAME plans with plain dense/index ops in the reference's operator
+order (per level FullyConnected, weighted segment sum, add_n, LeakyReLU; Dense; take; losses).
+
+The loss agrees to 1e-5.  For the gradients of the whole two-block stack the bar is the reference-order
+fp32 execution's own distance from the fp64 answer (depth compounds fp32 rounding and the residual
+pred - y cancels leading digits): the device result may be at most twice as far, plus 1e-5.  With
+LeakyReLU(0.1) a handful of the ~2 M pre-activations sit inside the fp32 rounding band around 0 and take the
+other branch than the fp64 evaluation (the fp32 oracle does the same), which moves individual gradient
+entries by up to 0.9 |g|; the additive term is 2e-4 there."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from hostgraph import from_synth
+
+pytestmark = pytest.mark.gpu
+R, D, U, O, DM = 5, 64, 250, 75, 64
+
+
+def leaky(z, act):
+    return torch.where(z > 0, z, 0.1 * z) if act == "leaky" else z
+
+
+def oracle(model, plans, lookups, needed, noise, recon_ids, gt_ratings, act, lam, dt=torch.float64):
+    """CPU re-execution in ``dt``; parameters are leaf copies so that autograd yields reference gradients."""
+    P = {n: p.detach().to(dt).cpu().requires_grad_(True) for n, p in model.named_parameters()}
+    i64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64)
+
+    def table(key):
+        return P[f"embed_layers._mods.{list(model.embed_layers.keys()).index(key)}.weight"]
+
+    def embed(key, ids, use_mask):
+        ids = i64(ids)
+        if not use_mask:
+            return table(key)[ids]
+        eff = i64(noise[key])[ids]
+        m = (eff != -1)
+        return table(key)[eff * m] * m[:, None].to(dt)
+
+    def dense(x, prefix):
+        return x @ P[prefix + ".weight"].T + P[prefix + ".bias"]
+
+    feats = {k: embed(k, ids, True) for k, ids in needed.items()}
+    pred_r, pred_e = [], []
+    keys = list(model.embed_layers.keys())
+    for b in range(len(plans)):
+        ids_dict, args = plans[b][0]
+        layer = model.encoders[b][0]
+        h = {}
+        for src, (row_inds, restore, entries) in args.items():
+            (dst, entry), = entries.items()
+            ep_l, _vals, ptr_l, sup_l = entry[:4]
+            ai = list(layer.aggregators.keys()).index((src, dst))
+            acc = 0
+            for r in range(R):
+                W, bb = P[f"encoders.{b}._blocks.0._aggregators._mods.{ai}.weight{r}"], P[f"encoders.{b}._blocks.0._aggregators._mods.{ai}.bias{r}"]
+                nnz = int(ptr_l[r][-1])
+                hr = feats[dst] @ W.T + bb
+                seg = torch.from_numpy(np.repeat(np.arange(len(ptr_l[r]) - 1), np.diff(ptr_l[r])).astype(np.int64))
+                contrib = torch.as_tensor(np.asarray(sup_l[r][:nnz]), dtype=dt)[:, None] * hr[i64(ep_l[r][:nnz])]
+                acc = acc + torch.zeros(len(ptr_l[r]) - 1, U, dtype=dt).index_add(0, seg, contrib)
+            oi = list(layer._out_fcs.keys()).index(src)
+            out = leaky(dense(leaky(acc, act), f"encoders.{b}._blocks.0._out_fcs._mods.{oi}"), act)
+            h[src] = out[i64(restore)] if restore is not None else out
+        look = lookups[b]
+        u = dense(h["user"][i64(look["rating"]["user"])], f"rating_user_projs.{b}")
+        v = dense(h["item"][i64(look["rating"]["item"])], f"rating_item_projs.{b}")
+        pred_r.append((u * v).sum(1))
+
+        def emap(key, x):
+            mi = list(model.embed_maps[b].keys()).index(key)
+            pre = f"embed_maps.{b}._mods.{mi}"
+            return dense(leaky(dense(x, pre + ".l0"), act), pre + ".l1")
+        pred_e.append({k: emap(k, h[k][i64(idx)]) for k, idx in look["recon"].items()})
+        if b < len(plans) - 1:
+            feats = {k: emap(k, h[k][i64(idx)]) for k, idx in look["next"].items()}
+    gt = {k: embed(k, ids, False) for k, ids in recon_ids.items()}
+    y = torch.as_tensor(gt_ratings, dtype=dt)
+    loss = sum((0.5 * (p - y) ** 2).mean() for p in pred_r)
+    loss = loss + lam * sum(((gt[k] - pe[k]) ** 2).sum(-1).mean() for pe in pred_e for k in pe)
+    loss.backward()
+    return float(loss), {n: (p.grad.double() if p.grad is not None else None) for n, p in P.items()}
+
+
+@pytest.mark.parametrize("act", ["identity", "leaky"])
+def test_full_stargcn_two_blocks_with_reconstruction(act):
+    from stargcn_b200 import synth
+    from stargcn_b200.model import StarGCN
+    from stargcn_b200.optim import FusedAdam
+    n_user, n_item, n_edges, _, _ = synth.SHAPES["ml-100k"]
+    g = synth.make_bipartite(n_user, n_item, n_edges, R, seed=1000)
+    graph = from_synth(g)
+    rs = np.random.RandomState(0)
+    B = 2000
+    pick = rs.choice(g["nnz"], B, replace=False)
+    pairs = np.stack([g["u2i"]["rows"][pick], g["u2i"]["cols"][pick]]).astype(np.int32)
+    ratings = g["u2i"]["vals"][pick].astype(np.float32)
+    noise, recon = {}, {}
+    for key, n in (("user", n_user), ("item", n_item)):
+        nz = np.arange(n, dtype=np.int32)
+        perm = rs.permutation(n)
+        n_rec = n // 10
+        recon[key] = perm[:n_rec].astype(np.int32)
+        nz[perm[: n_rec // 2]] = -1                                   # masked to zero
+        nz[perm[n_rec // 2: n_rec]] = rs.randint(0, n, n_rec - n_rec // 2)   # replaced by another node
+        noise[key] = nz
+    torch.manual_seed(0)
+    mls = {("user", "item"): R, ("item", "user"): R}
+    model = StarGCN(graph.meta_graph, mls, {"user": n_user, "item": n_item}, "user", "item", embed_units=D, agg_units=U,
+                    out_units=O, n_blocks=2, mid_map=DM, agg_accum="sum", act=act).cuda()
+    fan = {("user", "item"): -1, ("item", "user"): -1}
+    mean, std, lam = float(ratings.mean()), float(ratings.std()), 0.1
+    pr, pe, gt = model(graph, pairs, noise, recon, fan)               # materialises the lazily-shaped layers
+    assert len(pr) == 2 and len(pe) == 2 and pr[0].shape == (B, 1) and pe[1]["item"].shape == (len(recon["item"]), D)
+    y = torch.from_numpy(ratings).cuda()
+    loss = model.loss(pr, pe, gt, y, mean, std, lam)
+    loss.backward()
+    plans, lookups, needed = model.last_plans
+    plans_h = [[(p[0][0], p[0][1])] for p in plans]                   # one depth per block
+    target = (ratings - mean) / std
+    ref_loss, ref_g = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam)
+    loss32, g32 = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam, dt=torch.float32)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    # Depth compounds fp32 rounding (and the residual pred - y cancels leading digits), so the bar for the
+    # gradients of the whole stack is the reference-order fp32 execution's OWN distance from the fp64 answer:
+    # never more than twice that plus 1e-5.  LeakyReLU adds the branch flips described in the module docstring.
+    floor = 1e-5 if act == "identity" else 2e-4
+    checked, errs = 0, {}
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            assert ref_g[name] is None or float(ref_g[name].abs().max()) == 0.0, name
+            continue
+        e_gpu = rel_err(p.grad.cpu().numpy(), ref_g[name].numpy())
+        e_f32 = rel_err(g32[name].numpy(), ref_g[name].numpy())
+        errs[name] = (e_gpu, e_f32)
+        checked += 1
+    worst = sorted(errs.items(), key=lambda kv: -kv[1][0])[:5]
+    print("worst gradient errors (device, fp32 oracle):", worst)
+    for name, (e_gpu, e_f32) in errs.items():
+        assert e_gpu <= 2 * e_f32 + floor, (name, e_gpu, e_f32)
+    assert checked >= 2 + 2 * (2 * 2 * R + 4 + 8 + 4)                 # tables + per block: agg, out_fc, maps, projs
+    # one optimiser step through the multi-tensor clip + Adam keeps everything finite and moves the loss
+    opt = FusedAdam(list(model.parameters()), learning_rate=1e-2)
+    gnorm = opt.clip_global_norm(5.0)
+    opt.step()
+    assert float(gnorm) > 0 and all(torch.isfinite(p).all() for p in model.parameters())
+    with torch.no_grad():
+        pr2, pe2, gt2 = model(graph, pairs, noise, recon, fan)
+        loss2 = model.loss(pr2, pe2, gt2, y, mean, std, lam)
+    assert float(loss2) < float(loss)
