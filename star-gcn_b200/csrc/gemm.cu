@@ -137,13 +137,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 //
 // Accumulation accuracy: the tensor core adds into its fp32 TMEM accumulator with truncation
 // (measured: a 252-MMA chain at K=650 lands 3.5e-6 relative BELOW the exact magnitude, always
-// toward zero).  To stay well inside the 1e-5 parity bar at any K, a TMEM accumulator only ever
-// holds a chain of kChainKBlocks k-blocks (96 MMAs, <= 1.5e-6); the epilogue warps drain it
-// (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest while the MMA
-// warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).  Shorter chains cost
-// time (the drain is exposed: chain 2 -> 8 takes the forward GEMM from 0.155 to 0.119 ms).
+// toward zero; about 2e-8 relative per accumulating MMA).  To stay well inside the 1e-5 parity bar at
+// any K, a TMEM accumulator only ever holds a chain of kChainKBlocks k-blocks (48 MMAs, <= 1e-6); the
+// epilogue warps drain it (tcgen05.ld) and add it into fp32 REGISTER accumulators with round-to-nearest
+// while the MMA warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).  The chain
+// length trades time for accuracy — forward transform / error of one fused layer vs the fp64 answer:
+//   chain 2: 0.160 ms / 7.7e-7    chain 4: 0.136 ms / 8.8e-7    chain 8: 0.122 ms / 1.3e-6
+// (a plain fp32 FMA GEMM is at 1e-7 .. 3e-7).  Tuning knob: SG_GEMM_CHAIN.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChainKBlocks = 8;  // 8 k-blocks x 3 hi/lo products x 4 = 96 MMAs per TMEM chain
+constexpr int kChainKBlocks = 4;  // 4 k-blocks x 3 hi/lo products x 4 = 48 MMAs per TMEM chain
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
