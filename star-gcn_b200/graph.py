@@ -10,6 +10,7 @@ schedules that the backward pass needs, and stay resident for every forward/back
 uses the plan.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -328,6 +329,36 @@ class _FusedAggTransform(torch.autograd.Function):
                                            D, 1, plan, chunk, pp, _stream()), "sg_multilink_agg_bwd")
             _prof_end("agg_bwd", e0, csr)
         return gx, gw, None, None, None
+
+
+class _PackWExt(torch.autograd.Function):
+    """w_ext [U, R*D + R] = [W_0 | ... | W_{R-1} | b_0 ... b_{R-1}] from the per-level parameters.
+
+    Same values as ``torch.cat(ws + [torch.stack(bs, 1)], 1)``; what differs is the backward: autograd's
+    cat/stack backward hands every parameter a strided slice that AccumulateGrad then clones — 2R+1 tiny
+    launches per layer direction at the tail of the step.  Here the packed gradient is regrouped by TWO
+    launches into a level-major buffer whose contiguous rows ``gW[r]`` / ``gb[r]`` become the parameter
+    gradients directly."""
+
+    @staticmethod
+    def forward(ctx, R, *params):
+        ws, bs = params[:R], params[R:]
+        ctx.dims = (R,) + tuple(ws[0].shape)
+        return torch.cat(list(ws) + [torch.stack(bs, dim=1)], dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        R, U, D = ctx.dims
+        gw = g[:, :R * D].reshape(U, R, D).permute(1, 0, 2).contiguous()    # [R, U, D]
+        gb = g[:, R * D:].t().contiguous()                                  # [R, U]
+        return (None,) + tuple(gw[r] for r in range(R)) + tuple(gb[r] for r in range(R))
+
+
+def pack_w_ext(ws, bs):
+    """[W_0 | ... | W_{R-1} | b_0 ... b_{R-1}] — the B operand of the fused transform (see _PackWExt)."""
+    if os.environ.get("SG_PACK_FUSED", "1") == "0":       # A/B switch: autograd's own cat/stack backward
+        return torch.cat(list(ws) + [torch.stack(list(bs), dim=1)], dim=1)
+    return _PackWExt.apply(len(ws), *ws, *bs)
 
 
 def fused_agg_transform(x, w_ext, csr, slope, grad_group=None):

@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import seg_op
-from ..graph import FUSED_DIMS, MultiLinkCSR, fused_agg_transform, multilink_aggregate
+from ..graph import FUSED_DIMS, MultiLinkCSR, fused_agg_transform, multilink_aggregate, pack_w_ext
 from .common import activation_code, get_activation, xavier_in_uniform_
 
 
@@ -130,7 +130,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
         code = activation_code(self._act)
         if (self._accum == "sum" or self._num_links == 1) and D in FUSED_DIMS and code is not None and self.tensor_cores:
             # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
-            w_ext = torch.cat(ws + [torch.stack(bs, dim=1)], dim=1)   # (U, R*D + R)
+            w_ext = pack_w_ext(ws, bs)                                # (U, R*D + R)
             return fused_agg_transform(neighbor_data, w_ext, csr, {0: 1.0, 1: 0.1, 2: 0.0}[code], self.grad_group)
         agg, wsum = multilink_aggregate(neighbor_data, csr)           # (n_dst, R*D), (n_dst, R)
         if self._accum == "sum" or self._num_links == 1:
