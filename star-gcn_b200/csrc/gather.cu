@@ -63,8 +63,16 @@ __device__ __forceinline__ void st_row(float *p, const float (&v)[VEC]) {
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-__device__ __forceinline__ void store_wsum(const GatherArgs &a, int seg, float wacc) {
-  const int r = seg / a.n_out_rows, i = seg - r * a.n_out_rows;
+// r = seg / n_out_rows for 0 <= seg < 2^31 by multiply-high (Granlund-Montgomery round-up method:
+// shift = ceil(log2 d), magic = floor(2^32 (2^shift - d) / d) + 1, q = (mulhi(magic, n) + n) >> shift; the
+// sum cannot overflow because mulhi(magic, n) < n < 2^31).  The hardware has no integer divide: the
+// compiler's expansion costs ~30 instructions per segment, which the short user-side segments (11 edges)
+// paid twice — row offset and weight-sum offset.
+__device__ __forceinline__ int seg_rel(const GatherArgs &a, int seg) {
+  return (int)((__umulhi(a.div_magic, (uint32_t)seg) + (uint32_t)seg) >> a.div_shift);
+}
+
+__device__ __forceinline__ void store_wsum_at(const GatherArgs &a, int i, int r, float wacc) {
   const long long o = (long long)i * a.wsum_ld + r;
   if (a.wsum_lo) {
     const float h = tf32_hi(wacc);
@@ -75,9 +83,14 @@ __device__ __forceinline__ void store_wsum(const GatherArgs &a, int seg, float w
   }
 }
 
+__device__ __forceinline__ void store_wsum(const GatherArgs &a, int seg, float wacc) {
+  const int r = seg_rel(a, seg);
+  store_wsum_at(a, seg - r * a.n_out_rows, r, wacc);
+}
+
 __device__ __forceinline__ long long out_offset(const GatherArgs &a, int seg) {
   if (a.n_out_rows == a.n_seg) return (long long)seg * a.ld_out;
-  int r = seg / a.n_out_rows, i = seg - r * a.n_out_rows;
+  const int r = seg_rel(a, seg), i = seg - r * a.n_out_rows;
   return (long long)i * a.ld_out + (long long)r * a.F;
 }
 
@@ -202,7 +215,7 @@ __device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *_
 // (v * LPR + l) * 4, so each of the NV load instructions of a group touches LPR * 16 contiguous bytes.
 // NV = 2 at D = 64 puts FOUR work items in a warp instead of two: half the issued instructions per
 // edge, which is what bounds the short-segment (user-side) launch.
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
 __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs a) {
   constexpr int F = LPR * NV * 4;
   const int lane = threadIdx.x & (LPR - 1);
@@ -284,15 +297,20 @@ __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs 
       for (int v = 0; v < NV; ++v) reinterpret_cast<float4 *>(prow)[v * LPR + lane] = acc[v];
       if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
     } else {
-      float *orow = out + out_offset(a, d.z);
-      const float inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
+      int rel = 0, row = d.z;  // segment = rel * n_out_rows + row (relation-major concatenated CSRs)
+      if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
+      float *orow = out + ((long long)row * a.ld_out + rel * F);
+      float inv = 1.f;
+      if constexpr (!PLAIN) inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         float4 r = acc[v];
-        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
-        if (a.req == SG_REQ_ADD) {
-          const float4 o = reinterpret_cast<const float4 *>(orow)[v * LPR + lane];
-          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        if constexpr (!PLAIN) {  // PLAIN: req == write and no mean (the fused aggregation's two launches)
+          if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+          if (a.req == SG_REQ_ADD) {
+            const float4 o = reinterpret_cast<const float4 *>(orow)[v * LPR + lane];
+            r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+          }
         }
         if (a.out_lo) {
           const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
@@ -303,7 +321,121 @@ __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs 
           reinterpret_cast<float4 *>(orow)[v * LPR + lane] = r;
         }
       }
-      if (WSUM && lane == 0) store_wsum(a, d.z, wacc);
+      if (WSUM && lane == 0) store_wsum_at(a, row, rel, wacc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cooperative variant of the fast path (NV = 1): the LPR lanes of a group fetch the indices and weights
+// of up to LPR consecutive edges of their work item with ONE coalesced load each (lane l holds edge
+// base + l; the next LPR edges are prefetched while the current ones are processed) and hand them round
+// with warp shuffles, instead of every lane re-loading every index and weight (two uniform loads per
+// edge).  Control flow is warp-uniform — the groups of a warp step through max(len) edges together, short
+// groups predicated off — so the shuffles run with the full mask and no convergence check.  The row
+// loads, the order of the additions and therefore the results are those of gather_rows_fast_kernel bit
+// for bit.  Selected with SG_GATHER_SHAPE=4 (batches of 4) / 5 (batches of 8) / 6 (short segments only).
+// ------------------------------------------------------------------------------------------
+template <int LPR, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
+__global__ void __launch_bounds__(256) gather_rows_coop_kernel(const GatherArgs a) {
+  static_assert(LPR % UNROLL == 0 && LPR <= 32, "a batch never straddles the group's register window");
+  constexpr int F = LPR * 4;
+  constexpr int GPW = 32 / LPR;  // groups per warp
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & (LPR - 1);
+  const int sub = (threadIdx.x & 31) / LPR;
+  const int warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW;  // first group of this warp
+  const int n_groups = (gridDim.x * blockDim.x) / LPR;
+  const int k = blockIdx.y;
+
+  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src + (long long)k * a.src_batch_stride) + lane;
+  const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
+  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
+  const int32_t *__restrict__ idx = a.idx;
+  constexpr int ld4 = F / 4;
+  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
+
+  for (int it0 = warp0; it0 < n_items; it0 += n_groups) {  // warp-uniform
+    const int it = it0 + sub;
+    const bool live = it < n_items;
+    int4 d = make_int4(0, 0, 0, -1);
+    if (live) {
+      if (a.hdr) d = __ldg(a.items + it);
+      else d = make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
+    }
+    const int len = d.y - d.x;
+    int len_w = len;  // longest item of the warp
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) len_w = max(len_w, __shfl_xor_sync(kFull, len_w, o));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wacc = 0.f;
+    int nid = -1;
+    float nw = 0.f;
+    if (lane < len) {
+      nid = __ldg(idx + d.x + lane);
+      nw = edge_weight<WMODE>(a, w, d.x + lane, nid);
+    }
+    for (int off = 0; off < len_w; off += LPR) {  // warp-uniform
+      const int my_id = nid;  // edge d.x + off + lane, or -1 past the end of this group's item
+      const float my_w = nw;
+      nid = -1;
+      nw = 0.f;
+      if (off + LPR + lane < len) {  // prefetch the next window
+        nid = __ldg(idx + d.x + off + LPR + lane);
+        nw = edge_weight<WMODE>(a, w, d.x + off + LPR + lane, nid);
+      }
+      const int n_w = min(LPR, len_w - off);
+      for (int e = 0; e < n_w; e += UNROLL) {  // warp-uniform; e + u < LPR because LPR % UNROLL == 0
+        int id[UNROLL];
+        float wv[UNROLL];
+        float4 val[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) id[u] = __shfl_sync(kFull, my_id, e + u, LPR);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)  // a masked slot re-reads a row this batch already touches (an L1 hit, never used)
+          val[u] = __ldg(src + (long long)(id[u] >= 0 ? id[u] : max(id[0], 0)) * ld4);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) wv[u] = __shfl_sync(kFull, my_w, e + u, LPR);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (id[u] >= 0) {  // ascending edge order, one accumulator: the serial loop's additions
+            if constexpr (WSUM) wacc += wv[u];
+            acc.x = fmaf(wv[u], val[u].x, acc.x);
+            acc.y = fmaf(wv[u], val[u].y, acc.y);
+            acc.z = fmaf(wv[u], val[u].z, acc.z);
+            acc.w = fmaf(wv[u], val[u].w, acc.w);
+          }
+        }
+      }
+    }
+    if (!live) continue;
+
+    if (d.w >= 0) {
+      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * F;
+      reinterpret_cast<float4 *>(prow)[lane] = acc;
+      if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
+    } else {
+      int rel = 0, row = d.z;
+      if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
+      float *orow = out + ((long long)row * a.ld_out + rel * F);
+      float4 r = acc;
+      if constexpr (!PLAIN) {
+        const float inv = (a.mean && len > 0) ? 1.f / (float)len : 1.f;
+        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+        if (a.req == SG_REQ_ADD) {
+          const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
+          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        }
+      }
+      if (a.out_lo) {
+        const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
+        reinterpret_cast<float4 *>(orow)[lane] = hi;
+        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] =
+            make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
+      } else {
+        reinterpret_cast<float4 *>(orow)[lane] = r;
+      }
+      if (WSUM && lane == 0) store_wsum_at(a, row, rel, wacc);
     }
   }
 }
@@ -412,7 +544,7 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
@@ -420,7 +552,7 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM><<<grid, kThreads, 0, st>>>(a);
+  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
   SG_LAUNCHED("gather_rows_fast_kernel");
   if (a.hdr && n_long_cap > 0) {
     long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
@@ -432,13 +564,48 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   return SG_OK;
 }
 
+template <int LPR, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
+static int launch_coop(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  constexpr int kThreads = 256;
+  constexpr int groups_per_block = kThreads / LPR;
+  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)K, 1);
+  gather_rows_coop_kernel<LPR, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
+  SG_LAUNCHED("gather_rows_coop_kernel");
+  if (a.hdr && n_long_cap > 0) {
+    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
+    if (cb > cap) cb = cap;
+    dim3 cgrid((unsigned)cb, (unsigned)K, 1);
+    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
+    SG_LAUNCHED("combine_partials_kernel");
+  }
+  return SG_OK;
+}
+
+template <int LPR, int UNROLL>
+static int dispatch_coop_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  if (a.inv_len_indptr) return launch_coop<LPR, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
+  if (!a.w) return launch_coop<LPR, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.perm) return launch_coop<LPR, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
+  const bool plain = !a.mean && a.req == SG_REQ_WRITE;
+  if (a.wsum) return plain ? launch_coop<LPR, UNROLL, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
+                           : launch_coop<LPR, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
+  return plain ? launch_coop<LPR, UNROLL, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
+               : launch_coop<LPR, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
+}
+
 template <int LPR, int NV, int UNROLL>
 static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   if (a.inv_len_indptr) return launch_fast<LPR, NV, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
   if (!a.w) return launch_fast<LPR, NV, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
   if (a.perm) return launch_fast<LPR, NV, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
-  if (a.wsum) return launch_fast<LPR, NV, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
+  const bool plain = !a.mean && a.req == SG_REQ_WRITE;
+  if (a.wsum) return plain ? launch_fast<LPR, NV, UNROLL, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
+                           : launch_fast<LPR, NV, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
+  return plain ? launch_fast<LPR, NV, UNROLL, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
+               : launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
 }
 
 // Tuning knob (development only): SG_GATHER_SHAPE=1|2|3 forces a lane layout / batch size of the D=64 fast path.
@@ -453,6 +620,13 @@ static int gather_shape() {
 
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
   a.n_seg = n_seg;
+  if (a.n_out_rows > 0) {  // multiply-high constants of seg / n_out_rows (seg_rel)
+    const uint32_t d = (uint32_t)a.n_out_rows;
+    int l = 0;
+    while (l < 31 && (1u << l) < d) ++l;
+    a.div_shift = l;
+    a.div_magic = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  }
   int n_items_cap = n_seg, n_long_cap = 0;
   if (plan) {
     // header fields live on the device; size the grids from the host-side capacity bounds
@@ -483,6 +657,12 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
         if (gather_shape() == 1) return dispatch_fast_mode<8, 2, 4>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 2) return dispatch_fast_mode<8, 2, 8>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 3) return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 4) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 5) return dispatch_coop_mode<16, 8>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 6) {  // cooperative on the short-segment launches only
+          if (nnz < 16LL * n_items_cap) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
+          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+        }
         // short segments (fewer than 16 edges per work item on average, the user side of a rating graph):
         // batches of 4 waste fewer predicated tail slots than batches of 8 (0.303 -> 0.292 ms)
         if (nnz < 16LL * n_items_cap) return dispatch_fast_mode<16, 1, 4>(a, K, n_items_cap, n_long_cap, st);

@@ -12,6 +12,9 @@ struct GatherArgs {
   long long out_batch_stride = 0;
   int ld_out = 0;
   int n_out_rows = 0;
+  // seg / n_out_rows without an integer division (filled by run_gather; see seg_rel in gather.cu)
+  uint32_t div_magic = 0;
+  int div_shift = 0;
   // gathered matrix
   const float *src = nullptr;
   long long src_batch_stride = 0;
