@@ -537,12 +537,20 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
     for ev in free:
         ev.record()
 
+    # per-resource breakdown (reported, not part of the metric): event pairs around the copies on the copy
+    # stream and around the compute on the main stream, read after the timed region
+    copy_ev, comp_ev = [], []
+
     def issue_copy(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(free[slot])          # the compute that last read this slot has finished
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(copy_stream)
             for side in host:
                 for k, t in host[side].items():
                     slots[slot][side][k].copy_(t, non_blocking=True)
+            c1.record(copy_stream)
+            copy_ev.append((c0, c1))
             ready[slot].record(copy_stream)
 
     counter = [0]
@@ -554,6 +562,8 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
         main = torch.cuda.current_stream()
         main.wait_event(ready[slot])
         issue_copy((i + 1) % 2)                         # prefetch the next step's inputs
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(main)
         total = torch.zeros((), device=dev)
         for side in ("user", "item"):
             b, s = slots[slot][side], sides[side]
@@ -567,6 +577,8 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
             loss.backward()
             total = total + loss.detach()
         free[slot].record(main)
+        g1.record(main)
+        comp_ev.append((g0, g1))
         return float(total.item())   # D2H read of the step's result
 
     steps = max(3, min(args.steps, 50))
@@ -574,6 +586,7 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
     for _ in range(4):
         step()
     barrier()
+    del copy_ev[:], comp_ev[:]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -581,13 +594,20 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
+    h2d_ms = sum(a.elapsed_time(b) for a, b in copy_ev) / max(len(copy_ev), 1)
+    gpu_ms = sum(a.elapsed_time(b) for a, b in comp_ev) / max(len(comp_ev), 1)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return dict(value=total_edges / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
-                d2h_bytes_per_step=4, includes="H2D of CSR+features from pinned memory (double-buffered: the next step's copy overlaps this step's compute), device plan rebuild "
+                d2h_bytes_per_step=4,
+                breakdown=dict(h2d_ms=round(h2d_ms, 4), h2d_gbs=round(h2d / (h2d_ms * 1e-3) / 1e9, 2) if h2d_ms else None,
+                               gpu_compute_ms=round(gpu_ms, 4),
+                               note="copy-stream and compute-stream busy time per step (they overlap); the step time "
+                                    "also contains host launch latency and the blocking loss read-back"),
+                includes="H2D of CSR+features from pinned memory (double-buffered: the next step's copy overlaps this step's compute), device plan rebuild "
                 "(transpose + schedules), " + ("halo exchange, " if world > 1 else "") + "fwd+bwd, scalar loss read-back"
                 + ("; per rank, halo index plan reused" if world > 1 else ""))
 
