@@ -143,12 +143,18 @@ def test_full_stargcn_two_blocks_with_reconstruction(act):
     worst = sorted(errs.items(), key=lambda kv: -kv[1][0])[:5]
     print("worst gradient errors (device, fp32 oracle):", worst)
     assert checked >= 2 + 2 * (2 * 2 * R + 4 + 8 + 4)                 # tables + per block: agg, out_fc, maps, projs
-    # one optimiser step through the multi-tensor clip + Adam keeps everything finite and moves the loss
-    opt = FusedAdam(list(model.parameters()), learning_rate=1e-2)
-    gnorm = opt.clip_global_norm(5.0)
+    # one optimiser step through the multi-tensor clip + Adam with the reference's own hyper-parameters for this
+    # config (LR 0.002, GRAD_CLIP 1.0: experiments/cfg/transductive_ml_100k.yml:48,54) keeps everything finite,
+    # lowers the loss, and the loss at the NEW parameters again matches the fp64 re-execution.  (Adam's first step
+    # moves every weight by ~lr * sign(g); at lr 1e-2 the purely linear 'identity' stack overshoots — the fp64
+    # oracle shows the same 1.085 -> 1.163 — so the step size is the reference's, not an arbitrary one.)
+    opt = FusedAdam(list(model.parameters()), learning_rate=2e-3)
+    gnorm = opt.clip_global_norm(1.0)
     opt.step()
     assert float(gnorm) > 0 and all(torch.isfinite(p).all() for p in model.parameters())
     with torch.no_grad():
         pr2, pe2, gt2 = model(graph, pairs, noise, recon, fan)
         loss2 = model.loss(pr2, pe2, gt2, y, mean, std, lam)
     assert float(loss2) < float(loss)
+    ref_loss2, _ = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam)
+    assert abs(float(loss2) - ref_loss2) <= 1e-5 * abs(ref_loss2)
