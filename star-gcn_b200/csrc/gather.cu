@@ -440,6 +440,130 @@ __global__ void __launch_bounds__(256) gather_rows_coop_kernel(const GatherArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Software-pipelined variant of the fast path (NV = 1).  ncu on the short-segment launch (the user side of
+// a rating graph: 11 edges per segment) shows gather_rows_fast_kernel neither issue- nor bandwidth-bound
+// (issue slots 40 % busy, 5.5 TB/s through the L2->SM crossbar of the ~11 TB/s the long-segment launches
+// reach) but waiting on a CHAIN of dependent loads per work item: item descriptor -> indices -> rows, and
+// again indices -> rows for every following batch, because the in-order warp reaches the next batch's
+// index loads only after the FMAs that wait for the current rows.  Here
+//   * the next work item's descriptor is fetched while the current item is processed, and
+//   * batches of 4 edges alternate between two register buffers: the indices, weights AND rows of batch
+//     b+1 are requested before the FMAs of batch b, so up to 8 rows per lane group are in flight and a
+//     segment costs one index latency plus one row latency instead of one pair per batch.
+// Slots past the end of the item re-request the item's last row (merged with it in L1, never used);
+// their FMAs are predicated off, so additions happen in ascending edge order on one accumulator exactly
+// as in gather_rows_fast_kernel — results are bit-identical.
+// ------------------------------------------------------------------------------------------
+template <int LPR, int WMODE>
+__device__ __forceinline__ int pipe_load(const GatherArgs &a, const float4 *__restrict__ src, const float *__restrict__ w,
+                                         const int32_t *__restrict__ idx, int p, int end, float4 (&v)[4], float (&wv)[4]) {
+  constexpr int ld4 = LPR;
+  const int n = min(4, end - p);  // >= 1
+  int id[4];
+  // slots past the end re-read the item's LAST edge (clamped position): four independent, unpredicated
+  // index loads — a predicated load with a fallback value would chain each slot to the one before it
+#pragma unroll
+  for (int u = 0; u < 4; ++u) id[u] = __ldg(idx + min(p + u, end - 1));
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (long long)id[u] * ld4);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) wv[u] = edge_weight<WMODE>(a, w, min(p + u, end - 1), id[u]);
+  return n;
+}
+
+template <bool WSUM>
+__device__ __forceinline__ void pipe_fma(float4 &acc, float &wacc, const float4 (&v)[4], const float (&wv)[4], int n) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (u < n) {
+      if constexpr (WSUM) wacc += wv[u];
+      acc.x = fmaf(wv[u], v[u].x, acc.x);
+      acc.y = fmaf(wv[u], v[u].y, acc.y);
+      acc.z = fmaf(wv[u], v[u].z, acc.z);
+      acc.w = fmaf(wv[u], v[u].w, acc.w);
+    }
+  }
+}
+
+template <int LPR, int WMODE, bool WSUM, bool PLAIN, int MINB>
+__global__ void __launch_bounds__(256, MINB) gather_rows_pipe_kernel(const GatherArgs a) {
+  constexpr int F = LPR * 4;
+  const int lane = threadIdx.x & (LPR - 1);
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int n_groups = (gridDim.x * blockDim.x) / LPR;
+  const int k = blockIdx.y;
+
+  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src + (long long)k * a.src_batch_stride) + lane;
+  const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
+  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
+  const int32_t *__restrict__ idx = a.idx;
+  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
+
+  auto load_item = [&](int it) -> int4 {
+    if (a.hdr) return __ldg(a.items + it);
+    return make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
+  };
+
+  int it = group;
+  if (it >= n_items) return;
+  int4 d = load_item(it);
+  for (; it < n_items; it += n_groups) {
+    int4 dn = d;
+    if (it + n_groups < n_items) dn = load_item(it + n_groups);  // the next work item's descriptor, early
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wacc = 0.f;
+    const int end = d.y;
+    int p = d.x;
+    if (p < end) {
+      float4 va[4], vb[4];
+      float wa[4], wb[4];
+      int na = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, va, wa), nb;
+      for (;;) {
+        p += 4;
+        nb = 0;
+        if (p < end) nb = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, vb, wb);
+        pipe_fma<WSUM>(acc, wacc, va, wa, na);
+        if (nb == 0) break;
+        p += 4;
+        na = 0;
+        if (p < end) na = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, va, wa);
+        pipe_fma<WSUM>(acc, wacc, vb, wb, nb);
+        if (na == 0) break;
+      }
+    }
+
+    if (d.w >= 0) {
+      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * F;
+      reinterpret_cast<float4 *>(prow)[lane] = acc;
+      if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
+    } else {
+      int rel = 0, row = d.z;
+      if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
+      float *orow = out + ((long long)row * a.ld_out + rel * F);
+      float4 r = acc;
+      if constexpr (!PLAIN) {
+        const float inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
+        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+        if (a.req == SG_REQ_ADD) {
+          const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
+          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        }
+      }
+      if (a.out_lo) {
+        const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
+        reinterpret_cast<float4 *>(orow)[lane] = hi;
+        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] =
+            make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
+      } else {
+        reinterpret_cast<float4 *>(orow)[lane] = r;
+      }
+      if (WSUM && lane == 0) store_wsum_at(a, row, rel, wacc);
+    }
+    d = dn;
+  }
+}
+
 // Second pass: fixed-order sum of the partial rows of every split segment.
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
@@ -584,6 +708,38 @@ static int launch_coop(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   return SG_OK;
 }
 
+template <int LPR, int MINB, int WMODE, bool WSUM, bool PLAIN = false>
+static int launch_pipe(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  constexpr int kThreads = 256;
+  constexpr int groups_per_block = kThreads / LPR;
+  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)K, 1);
+  gather_rows_pipe_kernel<LPR, WMODE, WSUM, PLAIN, MINB><<<grid, kThreads, 0, st>>>(a);
+  SG_LAUNCHED("gather_rows_pipe_kernel");
+  if (a.hdr && n_long_cap > 0) {
+    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
+    if (cb > cap) cb = cap;
+    dim3 cgrid((unsigned)cb, (unsigned)K, 1);
+    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
+    SG_LAUNCHED("combine_partials_kernel");
+  }
+  return SG_OK;
+}
+
+template <int LPR, int MINB>
+static int dispatch_pipe_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  if (a.inv_len_indptr) return launch_pipe<LPR, MINB, 3, false>(a, K, n_items_cap, n_long_cap, st);
+  if (!a.w) return launch_pipe<LPR, MINB, 0, false>(a, K, n_items_cap, n_long_cap, st);
+  if (a.perm) return launch_pipe<LPR, MINB, 2, false>(a, K, n_items_cap, n_long_cap, st);
+  const bool plain = !a.mean && a.req == SG_REQ_WRITE;
+  if (a.wsum) return plain ? launch_pipe<LPR, MINB, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
+                           : launch_pipe<LPR, MINB, 1, true>(a, K, n_items_cap, n_long_cap, st);
+  return plain ? launch_pipe<LPR, MINB, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
+               : launch_pipe<LPR, MINB, 1, false>(a, K, n_items_cap, n_long_cap, st);
+}
+
 template <int LPR, int UNROLL>
 static int dispatch_coop_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   if (a.inv_len_indptr) return launch_coop<LPR, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
@@ -659,6 +815,14 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
         if (gather_shape() == 3) return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 4) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 5) return dispatch_coop_mode<16, 8>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 7 || gather_shape() == 9) {  // software-pipelined on the short-segment launches only
+          if (nnz < 16LL * n_items_cap)
+            return gather_shape() == 7 ? dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st)
+                                       : dispatch_pipe_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
+          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+        }
+        if (gather_shape() == 8) return dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st);
+        if (gather_shape() == 10) return dispatch_pipe_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 6) {  // cooperative on the short-segment launches only
           if (nnz < 16LL * n_items_cap) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
           return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
