@@ -215,8 +215,8 @@ __device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *_
 // (v * LPR + l) * 4, so each of the NV load instructions of a group touches LPR * 16 contiguous bytes.
 // NV = 2 at D = 64 puts FOUR work items in a warp instead of two: half the issued instructions per
 // edge, which is what bounds the short-segment (user-side) launch.
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
-__global__ void __launch_bounds__(256) gather_rows_fast_kernel(const GatherArgs a) {
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) gather_rows_fast_kernel(const GatherArgs a) {
   constexpr int F = LPR * NV * 4;
   const int lane = threadIdx.x & (LPR - 1);
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -631,6 +631,14 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
   }
 }
 
+// Tuning knob (development only): SG_GATHER_GRID = blocks per SM the grid-stride kernels are launched with.
+static long long grid_cap() {  // read on every call: tools/sweep_gather.py changes it inside one process
+  const char *e = getenv("SG_GATHER_GRID");
+  int v = e ? atoi(e) : 16;
+  if (v < 1) v = 16;
+  return (long long)num_sms() * v;
+}
+
 template <int VEC, int LPR, int NV>
 static int launch_gather(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   constexpr int UNROLL = NV >= 2 ? 2 : 4;
@@ -638,7 +646,7 @@ static int launch_gather(const GatherArgs &a, int K, int n_items_cap, int n_long
   constexpr int groups_per_block = kThreads / LPR;
   const int col_chunks = ceil_div(a.F, LPR * NV * VEC);
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, (unsigned)col_chunks);
   gather_rows_kernel<VEC, LPR, NV, UNROLL><<<grid, kThreads, 0, st>>>(a);
@@ -668,15 +676,15 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false, int MINB = 1>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
+  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN, MINB><<<grid, kThreads, 0, st>>>(a);
   SG_LAUNCHED("gather_rows_fast_kernel");
   if (a.hdr && n_long_cap > 0) {
     long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
@@ -693,7 +701,7 @@ static int launch_coop(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
   gather_rows_coop_kernel<LPR, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
@@ -713,7 +721,7 @@ static int launch_pipe(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
   gather_rows_pipe_kernel<LPR, WMODE, WSUM, PLAIN, MINB><<<grid, kThreads, 0, st>>>(a);
@@ -752,26 +760,23 @@ static int dispatch_coop_mode(const GatherArgs &a, int K, int n_items_cap, int n
                : launch_coop<LPR, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
 }
 
-template <int LPR, int NV, int UNROLL>
+template <int LPR, int NV, int UNROLL, int MINB = 1>
 static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   if (a.inv_len_indptr) return launch_fast<LPR, NV, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
   if (!a.w) return launch_fast<LPR, NV, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
   if (a.perm) return launch_fast<LPR, NV, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
   const bool plain = !a.mean && a.req == SG_REQ_WRITE;
-  if (a.wsum) return plain ? launch_fast<LPR, NV, UNROLL, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
+  // MINB (minimum resident blocks per SM, i.e. a register cap) applies to the PLAIN instances only
+  if (a.wsum) return plain ? launch_fast<LPR, NV, UNROLL, 1, true, true, MINB>(a, K, n_items_cap, n_long_cap, st)
                            : launch_fast<LPR, NV, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return plain ? launch_fast<LPR, NV, UNROLL, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
+  return plain ? launch_fast<LPR, NV, UNROLL, 1, false, true, MINB>(a, K, n_items_cap, n_long_cap, st)
                : launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
 }
 
 // Tuning knob (development only): SG_GATHER_SHAPE=1|2|3 forces a lane layout / batch size of the D=64 fast path.
 static int gather_shape() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SG_GATHER_SHAPE");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+  const char *e = getenv("SG_GATHER_SHAPE");
+  return e ? atoi(e) : 0;
 }
 
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
@@ -819,6 +824,11 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
           if (nnz < 16LL * n_items_cap)
             return gather_shape() == 7 ? dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st)
                                        : dispatch_pipe_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
+          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+        }
+        if (gather_shape() == 11 || gather_shape() == 12) {  // register cap: 8 (7) resident blocks per SM
+          if (nnz < 16LL * n_items_cap) return dispatch_fast_mode<16, 1, 4, 8>(a, K, n_items_cap, n_long_cap, st);
+          if (gather_shape() == 12) return dispatch_fast_mode<16, 1, 8, 7>(a, K, n_items_cap, n_long_cap, st);
           return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
         }
         if (gather_shape() == 8) return dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st);

@@ -1,0 +1,82 @@
+"""Developer tool: time the four gather launches of one ML-10M-shaped step under tuning knobs, in one process.
+    python tools/sweep_gather.py "SG_GATHER_SHAPE=0" "SG_GATHER_SHAPE=11,SG_GATHER_GRID=8" ...
+Each argument is a comma-separated list of NAME=VALUE environment settings (read by gather.cu on every call)."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import stargcn_b200  # noqa: F401,E402
+from stargcn_b200 import _lib  # noqa: E402
+from stargcn_b200._lib import check  # noqa: E402
+from stargcn_b200.graph import MultiLinkCSR  # noqa: E402
+from stargcn_b200.seg_op import _p, _stream  # noqa: E402
+
+KNOBS = ("SG_GATHER_SHAPE", "SG_GATHER_GRID")
+
+
+def main():
+    configs = sys.argv[1:] or ["SG_GATHER_SHAPE=0"]
+    wl = bench.load_workload(os.environ.get("SWEEP_WORKLOAD", "ml-10m"))
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    R, D = wl["R"], wl["D"]
+    sides = []
+    for side, x_nb in (("user", wl["x_item"]), ("item", wl["x_user"])):
+        csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
+        x = torch.from_numpy(x_nb).to(dev)
+        ld = (R * D + R + 31) // 32 * 32
+        agg_hi = torch.empty((csr.n_dst, ld), device=dev)
+        agg_lo = torch.empty_like(agg_hi)
+        gagg = torch.randn((csr.n_dst, R * D), device=dev)
+        gx = torch.empty((csr.n_nb, D), device=dev)
+        sched, tsched = csr.schedule(), csr.t_schedule()
+        part, tpart = sched.partial(1, D, extra_per_row=1), tsched.partial(1, D)
+        t_indptr, t_src, t_w = csr.transposed()
+
+        def fwd(csr=csr, x=x, agg_hi=agg_hi, agg_lo=agg_lo, ld=ld, sched=sched, part=part):
+            check(lib.sg_multilink_agg_fwd_split(_p(agg_hi), _p(agg_lo), ld, _p(x), _p(csr.support), _p(csr.end_points),
+                                                 _p(csr.cat_indptr), R, csr.n_dst, csr.n_nb, csr.nnz, D, _p(sched.buf),
+                                                 sched.chunk, _p(part), _stream()), "fwd")
+
+        def bwd(csr=csr, gx=gx, gagg=gagg, t_w=t_w, t_src=t_src, t_indptr=t_indptr, tsched=tsched, tpart=tpart):
+            check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, csr.n_dst, csr.n_nb,
+                                           csr.nnz, D, 1, _p(tsched.buf), tsched.chunk, _p(tpart), _stream()), "bwd")
+        sides.append((side, fwd, bwd, agg_hi, gx))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ref = {}
+    print(f"{'config':44s} " + " ".join(f"{s}:{d:>4s}" for s in ("user", "item") for d in ("fwd", "bwd")) + "    sum(ms)")
+    for cfg in configs:
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        for kv in filter(None, cfg.split(",")):
+            k, v = kv.split("=")
+            os.environ[k] = v
+        times = []
+        for side, fwd, bwd, agg_hi, gx in sides:
+            for name, fn, outbuf in (("fwd", fwd, agg_hi), ("bwd", bwd, gx)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                tot = 0.0
+                for _ in range(10):
+                    flush.zero_()                      # evict the tables' L2 lines between repetitions
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(); e1.record()
+                    torch.cuda.synchronize()
+                    tot += e0.elapsed_time(e1)
+                times.append(tot / 10)
+                key = (side, name)
+                if key not in ref:
+                    ref[key] = outbuf.clone()
+                elif not torch.equal(ref[key], outbuf):
+                    print(f"   !! {cfg}: {side} {name} differs from the first configuration "
+                          f"(max abs {float((ref[key] - outbuf).abs().max()):.3e})")
+        print(f"{cfg:44s} " + " ".join(f"{t:9.4f}" for t in times) + f"   {sum(times):8.4f}")
+
+
+if __name__ == "__main__":
+    main()
