@@ -632,10 +632,14 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
 }
 
 // Tuning knob (development only): SG_GATHER_GRID = blocks per SM the grid-stride kernels are launched with.
+// Grid-stride launches use at most 32 blocks per SM (5-6 resident at a time): work items differ in length
+// (chunks of up to 256 edges), so several waves of smaller blocks balance better than one resident wave —
+// measured on the ML-10M shape, sum of the four launches: 0.99 ms at 6 blocks/SM, 0.86 at 16, 0.82 at
+// 24..64, 0.86 with one item per group (tools/sweep_gather.py).
 static long long grid_cap() {  // read on every call: tools/sweep_gather.py changes it inside one process
   const char *e = getenv("SG_GATHER_GRID");
-  int v = e ? atoi(e) : 16;
-  if (v < 1) v = 16;
+  int v = e ? atoi(e) : 32;
+  if (v < 1) v = 32;
   return (long long)num_sms() * v;
 }
 

@@ -46,9 +46,27 @@ def main():
             check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, csr.n_dst, csr.n_nb,
                                            csr.nnz, D, 1, _p(tsched.buf), tsched.chunk, _p(tpart), _stream()), "bwd")
         sides.append((side, fwd, bwd, agg_hi, gx))
+        if side == "user" and os.environ.get("SWEEP_LAYOUT"):
+            # layout experiment: the same gather (a) unsplit into the strided [n_dst, R*D] layout and (b) through
+            # seg_weighted_pool over the concatenated CSR into a contiguous [R*n_dst, D] (level-major) buffer
+            agg = torch.empty((csr.n_dst, R * D), device=dev)
+            wsum = torch.empty((csr.n_dst, R), device=dev)
+            flat = torch.empty((R * csr.n_dst, D), device=dev)
+            part0 = sched.partial(1, D)
+
+            def fwd_strided(csr=csr, x=x, agg=agg, wsum=wsum, sched=sched, part=part):
+                check(lib.sg_multilink_agg_fwd(_p(agg), _p(wsum), _p(x), _p(csr.support), _p(csr.end_points),
+                                               _p(csr.cat_indptr), R, csr.n_dst, csr.n_nb, csr.nnz, D, _p(sched.buf),
+                                               sched.chunk, _p(part), _stream()), "fwd_strided")
+
+            def fwd_contig(csr=csr, x=x, flat=flat, sched=sched, part0=part0):
+                check(lib.sg_weighted_pool_fwd(_p(flat), _p(x), _p(csr.support), _p(csr.end_points), _p(csr.cat_indptr),
+                                               1, R * csr.n_dst, csr.n_nb, csr.nnz, D, 1, _p(sched.buf), sched.chunk,
+                                               _p(part0), _stream()), "fwd_contig")
+            sides.append(("user[unsplit strided | contiguous]", fwd_strided, fwd_contig, agg, flat))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = {}
-    print(f"{'config':44s} " + " ".join(f"{s}:{d:>4s}" for s in ("user", "item") for d in ("fwd", "bwd")) + "    sum(ms)")
+    print(f"{'config':44s} " + " ".join(f"{s[0][:22]}:{d}" for s in sides for d in ("fwd", "bwd")) + "    sum(ms)")
     for cfg in configs:
         for k in KNOBS:
             os.environ.pop(k, None)
