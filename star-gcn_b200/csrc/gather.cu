@@ -215,8 +215,12 @@ __device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *_
 // (v * LPR + l) * 4, so each of the NV load instructions of a group touches LPR * 16 contiguous bytes.
 // NV = 2 at D = 64 puts FOUR work items in a warp instead of two: half the issued instructions per
 // edge, which is what bounds the short-segment (user-side) launch.
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN, int MINB = 1>
-__global__ void __launch_bounds__(256, MINB) gather_rows_fast_kernel(const GatherArgs a) {
+// __launch_bounds__(256, 1): no register cap.  The compiler then takes 46 (batches of 4) / 64 (batches of 8)
+// registers and issues the loads of a batch further ahead; with the 40-register build (6 resident blocks
+// instead of 4) the long-segment launches were 5 % slower, and a 32-register cap (64 resident warps) did not
+// help the short-segment launch either — none of them is occupancy-bound (profiles/r01_summary.md §H).
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
+__global__ void __launch_bounds__(256, 1) gather_rows_fast_kernel(const GatherArgs a) {
   constexpr int F = LPR * NV * 4;
   const int lane = threadIdx.x & (LPR - 1);
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -326,244 +330,6 @@ __global__ void __launch_bounds__(256, MINB) gather_rows_fast_kernel(const Gathe
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Cooperative variant of the fast path (NV = 1): the LPR lanes of a group fetch the indices and weights
-// of up to LPR consecutive edges of their work item with ONE coalesced load each (lane l holds edge
-// base + l; the next LPR edges are prefetched while the current ones are processed) and hand them round
-// with warp shuffles, instead of every lane re-loading every index and weight (two uniform loads per
-// edge).  Control flow is warp-uniform — the groups of a warp step through max(len) edges together, short
-// groups predicated off — so the shuffles run with the full mask and no convergence check.  The row
-// loads, the order of the additions and therefore the results are those of gather_rows_fast_kernel bit
-// for bit.  Selected with SG_GATHER_SHAPE=4 (batches of 4) / 5 (batches of 8) / 6 (short segments only).
-// ------------------------------------------------------------------------------------------
-template <int LPR, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
-__global__ void __launch_bounds__(256) gather_rows_coop_kernel(const GatherArgs a) {
-  static_assert(LPR % UNROLL == 0 && LPR <= 32, "a batch never straddles the group's register window");
-  constexpr int F = LPR * 4;
-  constexpr int GPW = 32 / LPR;  // groups per warp
-  constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & (LPR - 1);
-  const int sub = (threadIdx.x & 31) / LPR;
-  const int warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW;  // first group of this warp
-  const int n_groups = (gridDim.x * blockDim.x) / LPR;
-  const int k = blockIdx.y;
-
-  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src + (long long)k * a.src_batch_stride) + lane;
-  const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
-  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
-  const int32_t *__restrict__ idx = a.idx;
-  constexpr int ld4 = F / 4;
-  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
-
-  for (int it0 = warp0; it0 < n_items; it0 += n_groups) {  // warp-uniform
-    const int it = it0 + sub;
-    const bool live = it < n_items;
-    int4 d = make_int4(0, 0, 0, -1);
-    if (live) {
-      if (a.hdr) d = __ldg(a.items + it);
-      else d = make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
-    }
-    const int len = d.y - d.x;
-    int len_w = len;  // longest item of the warp
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) len_w = max(len_w, __shfl_xor_sync(kFull, len_w, o));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wacc = 0.f;
-    int nid = -1;
-    float nw = 0.f;
-    if (lane < len) {
-      nid = __ldg(idx + d.x + lane);
-      nw = edge_weight<WMODE>(a, w, d.x + lane, nid);
-    }
-    for (int off = 0; off < len_w; off += LPR) {  // warp-uniform
-      const int my_id = nid;  // edge d.x + off + lane, or -1 past the end of this group's item
-      const float my_w = nw;
-      nid = -1;
-      nw = 0.f;
-      if (off + LPR + lane < len) {  // prefetch the next window
-        nid = __ldg(idx + d.x + off + LPR + lane);
-        nw = edge_weight<WMODE>(a, w, d.x + off + LPR + lane, nid);
-      }
-      const int n_w = min(LPR, len_w - off);
-      for (int e = 0; e < n_w; e += UNROLL) {  // warp-uniform; e + u < LPR because LPR % UNROLL == 0
-        int id[UNROLL];
-        float wv[UNROLL];
-        float4 val[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) id[u] = __shfl_sync(kFull, my_id, e + u, LPR);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)  // a masked slot re-reads a row this batch already touches (an L1 hit, never used)
-          val[u] = __ldg(src + (long long)(id[u] >= 0 ? id[u] : max(id[0], 0)) * ld4);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) wv[u] = __shfl_sync(kFull, my_w, e + u, LPR);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          if (id[u] >= 0) {  // ascending edge order, one accumulator: the serial loop's additions
-            if constexpr (WSUM) wacc += wv[u];
-            acc.x = fmaf(wv[u], val[u].x, acc.x);
-            acc.y = fmaf(wv[u], val[u].y, acc.y);
-            acc.z = fmaf(wv[u], val[u].z, acc.z);
-            acc.w = fmaf(wv[u], val[u].w, acc.w);
-          }
-        }
-      }
-    }
-    if (!live) continue;
-
-    if (d.w >= 0) {
-      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * F;
-      reinterpret_cast<float4 *>(prow)[lane] = acc;
-      if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
-    } else {
-      int rel = 0, row = d.z;
-      if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
-      float *orow = out + ((long long)row * a.ld_out + rel * F);
-      float4 r = acc;
-      if constexpr (!PLAIN) {
-        const float inv = (a.mean && len > 0) ? 1.f / (float)len : 1.f;
-        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
-        if (a.req == SG_REQ_ADD) {
-          const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
-          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
-        }
-      }
-      if (a.out_lo) {
-        const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
-        reinterpret_cast<float4 *>(orow)[lane] = hi;
-        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] =
-            make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
-      } else {
-        reinterpret_cast<float4 *>(orow)[lane] = r;
-      }
-      if (WSUM && lane == 0) store_wsum_at(a, row, rel, wacc);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Software-pipelined variant of the fast path (NV = 1).  ncu on the short-segment launch (the user side of
-// a rating graph: 11 edges per segment) shows gather_rows_fast_kernel neither issue- nor bandwidth-bound
-// (issue slots 40 % busy, 5.5 TB/s through the L2->SM crossbar of the ~11 TB/s the long-segment launches
-// reach) but waiting on a CHAIN of dependent loads per work item: item descriptor -> indices -> rows, and
-// again indices -> rows for every following batch, because the in-order warp reaches the next batch's
-// index loads only after the FMAs that wait for the current rows.  Here
-//   * the next work item's descriptor is fetched while the current item is processed, and
-//   * batches of 4 edges alternate between two register buffers: the indices, weights AND rows of batch
-//     b+1 are requested before the FMAs of batch b, so up to 8 rows per lane group are in flight and a
-//     segment costs one index latency plus one row latency instead of one pair per batch.
-// Slots past the end of the item re-request the item's last row (merged with it in L1, never used);
-// their FMAs are predicated off, so additions happen in ascending edge order on one accumulator exactly
-// as in gather_rows_fast_kernel — results are bit-identical.
-// ------------------------------------------------------------------------------------------
-template <int LPR, int WMODE>
-__device__ __forceinline__ int pipe_load(const GatherArgs &a, const float4 *__restrict__ src, const float *__restrict__ w,
-                                         const int32_t *__restrict__ idx, int p, int end, float4 (&v)[4], float (&wv)[4]) {
-  constexpr int ld4 = LPR;
-  const int n = min(4, end - p);  // >= 1
-  int id[4];
-  // slots past the end re-read the item's LAST edge (clamped position): four independent, unpredicated
-  // index loads — a predicated load with a fallback value would chain each slot to the one before it
-#pragma unroll
-  for (int u = 0; u < 4; ++u) id[u] = __ldg(idx + min(p + u, end - 1));
-#pragma unroll
-  for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (long long)id[u] * ld4);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) wv[u] = edge_weight<WMODE>(a, w, min(p + u, end - 1), id[u]);
-  return n;
-}
-
-template <bool WSUM>
-__device__ __forceinline__ void pipe_fma(float4 &acc, float &wacc, const float4 (&v)[4], const float (&wv)[4], int n) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (u < n) {
-      if constexpr (WSUM) wacc += wv[u];
-      acc.x = fmaf(wv[u], v[u].x, acc.x);
-      acc.y = fmaf(wv[u], v[u].y, acc.y);
-      acc.z = fmaf(wv[u], v[u].z, acc.z);
-      acc.w = fmaf(wv[u], v[u].w, acc.w);
-    }
-  }
-}
-
-template <int LPR, int WMODE, bool WSUM, bool PLAIN, int MINB>
-__global__ void __launch_bounds__(256, MINB) gather_rows_pipe_kernel(const GatherArgs a) {
-  constexpr int F = LPR * 4;
-  const int lane = threadIdx.x & (LPR - 1);
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int n_groups = (gridDim.x * blockDim.x) / LPR;
-  const int k = blockIdx.y;
-
-  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src + (long long)k * a.src_batch_stride) + lane;
-  const float *__restrict__ w = WMODE == 1 || WMODE == 2 ? a.w + (long long)k * a.w_batch_stride : nullptr;
-  float *__restrict__ out = a.out + (long long)k * a.out_batch_stride;
-  const int32_t *__restrict__ idx = a.idx;
-  const int n_items = a.hdr ? a.hdr->n_items : a.n_seg;
-
-  auto load_item = [&](int it) -> int4 {
-    if (a.hdr) return __ldg(a.items + it);
-    return make_int4(__ldg(a.indptr + it), __ldg(a.indptr + it + 1), it, -1);
-  };
-
-  int it = group;
-  if (it >= n_items) return;
-  int4 d = load_item(it);
-  for (; it < n_items; it += n_groups) {
-    int4 dn = d;
-    if (it + n_groups < n_items) dn = load_item(it + n_groups);  // the next work item's descriptor, early
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wacc = 0.f;
-    const int end = d.y;
-    int p = d.x;
-    if (p < end) {
-      float4 va[4], vb[4];
-      float wa[4], wb[4];
-      int na = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, va, wa), nb;
-      for (;;) {
-        p += 4;
-        nb = 0;
-        if (p < end) nb = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, vb, wb);
-        pipe_fma<WSUM>(acc, wacc, va, wa, na);
-        if (nb == 0) break;
-        p += 4;
-        na = 0;
-        if (p < end) na = pipe_load<LPR, WMODE>(a, src, w, idx, p, end, va, wa);
-        pipe_fma<WSUM>(acc, wacc, vb, wb, nb);
-        if (na == 0) break;
-      }
-    }
-
-    if (d.w >= 0) {
-      float *prow = a.partial + (long long)k * a.partial_batch_stride + (long long)d.w * F;
-      reinterpret_cast<float4 *>(prow)[lane] = acc;
-      if (WSUM && lane == 0) a.partial_wsum[d.w] = wacc;
-    } else {
-      int rel = 0, row = d.z;
-      if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
-      float *orow = out + ((long long)row * a.ld_out + rel * F);
-      float4 r = acc;
-      if constexpr (!PLAIN) {
-        const float inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
-        if (a.mean) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
-        if (a.req == SG_REQ_ADD) {
-          const float4 o = reinterpret_cast<const float4 *>(orow)[lane];
-          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
-        }
-      }
-      if (a.out_lo) {
-        const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
-        reinterpret_cast<float4 *>(orow)[lane] = hi;
-        reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[lane] =
-            make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
-      } else {
-        reinterpret_cast<float4 *>(orow)[lane] = r;
-      }
-      if (WSUM && lane == 0) store_wsum_at(a, row, rel, wacc);
-    }
-    d = dn;
-  }
-}
-
 // Second pass: fixed-order sum of the partial rows of every split segment.
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
@@ -583,19 +349,38 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
 #pragma unroll
       for (int e = 0; e < VEC; ++e) acc[v][e] = 0.f;
     float wacc = 0.f;
-    for (int s = 0; s < d.z; ++s) {
-      const float *prow = partial + (long long)(d.y + s) * a.F;
+    // CU partial rows are requested before any is added (the hottest item of a rating graph is cut into
+    // hundreds of partials: one dependent load per partial made this pass 35 us); additions stay in slot order
+    constexpr int CU = NV * VEC <= 4 ? 8 : 2;
+    for (int s0 = 0; s0 < d.z; s0 += CU) {
+      float t[CU][NV][VEC];
+      float tw[CU];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = col0 + (v * LPR + lane) * VEC;
-        if (c < a.F) {
-          float t[VEC];
-          ld_plain<VEC>(t, prow + c);
+      for (int u = 0; u < CU; ++u) {
+        const bool ok = s0 + u < d.z;
+        const float *prow = partial + (long long)(d.y + s0 + u) * a.F;
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) acc[v][e] += t[e];
+        for (int v = 0; v < NV; ++v) {
+          const int c = col0 + (v * LPR + lane) * VEC;
+          if (ok && c < a.F) {
+            ld_plain<VEC>(t[u][v], prow + c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[u][v][e] = 0.f;
+          }
+        }
+        tw[u] = (ok && a.partial_wsum) ? a.partial_wsum[d.y + s0 + u] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        if (s0 + u < d.z) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[v][e] += t[u][v][e];
+          wacc += tw[u];
         }
       }
-      if (a.partial_wsum) wacc += a.partial_wsum[d.y + s];
     }
     float *orow = out + out_offset(a, d.x);
     float inv = 1.f;
@@ -680,7 +465,7 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false, int MINB = 1>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
@@ -688,7 +473,7 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN, MINB><<<grid, kThreads, 0, st>>>(a);
+  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
   SG_LAUNCHED("gather_rows_fast_kernel");
   if (a.hdr && n_long_cap > 0) {
     long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
@@ -700,80 +485,15 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   return SG_OK;
 }
 
-template <int LPR, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
-static int launch_coop(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  constexpr int kThreads = 256;
-  constexpr int groups_per_block = kThreads / LPR;
-  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = grid_cap();
-  if (blocks > cap) blocks = cap;
-  dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_coop_kernel<LPR, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
-  SG_LAUNCHED("gather_rows_coop_kernel");
-  if (a.hdr && n_long_cap > 0) {
-    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
-    if (cb > cap) cb = cap;
-    dim3 cgrid((unsigned)cb, (unsigned)K, 1);
-    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
-    SG_LAUNCHED("combine_partials_kernel");
-  }
-  return SG_OK;
-}
-
-template <int LPR, int MINB, int WMODE, bool WSUM, bool PLAIN = false>
-static int launch_pipe(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  constexpr int kThreads = 256;
-  constexpr int groups_per_block = kThreads / LPR;
-  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = grid_cap();
-  if (blocks > cap) blocks = cap;
-  dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_pipe_kernel<LPR, WMODE, WSUM, PLAIN, MINB><<<grid, kThreads, 0, st>>>(a);
-  SG_LAUNCHED("gather_rows_pipe_kernel");
-  if (a.hdr && n_long_cap > 0) {
-    long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
-    if (cb > cap) cb = cap;
-    dim3 cgrid((unsigned)cb, (unsigned)K, 1);
-    combine_partials_kernel<4, LPR, 1><<<cgrid, kThreads, 0, st>>>(a);
-    SG_LAUNCHED("combine_partials_kernel");
-  }
-  return SG_OK;
-}
-
-template <int LPR, int MINB>
-static int dispatch_pipe_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  if (a.inv_len_indptr) return launch_pipe<LPR, MINB, 3, false>(a, K, n_items_cap, n_long_cap, st);
-  if (!a.w) return launch_pipe<LPR, MINB, 0, false>(a, K, n_items_cap, n_long_cap, st);
-  if (a.perm) return launch_pipe<LPR, MINB, 2, false>(a, K, n_items_cap, n_long_cap, st);
-  const bool plain = !a.mean && a.req == SG_REQ_WRITE;
-  if (a.wsum) return plain ? launch_pipe<LPR, MINB, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
-                           : launch_pipe<LPR, MINB, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return plain ? launch_pipe<LPR, MINB, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
-               : launch_pipe<LPR, MINB, 1, false>(a, K, n_items_cap, n_long_cap, st);
-}
-
-template <int LPR, int UNROLL>
-static int dispatch_coop_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  if (a.inv_len_indptr) return launch_coop<LPR, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
-  if (!a.w) return launch_coop<LPR, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
-  if (a.perm) return launch_coop<LPR, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
-  const bool plain = !a.mean && a.req == SG_REQ_WRITE;
-  if (a.wsum) return plain ? launch_coop<LPR, UNROLL, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
-                           : launch_coop<LPR, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return plain ? launch_coop<LPR, UNROLL, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
-               : launch_coop<LPR, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
-}
-
-template <int LPR, int NV, int UNROLL, int MINB = 1>
+template <int LPR, int NV, int UNROLL>
 static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   if (a.inv_len_indptr) return launch_fast<LPR, NV, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
   if (!a.w) return launch_fast<LPR, NV, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
   if (a.perm) return launch_fast<LPR, NV, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
   const bool plain = !a.mean && a.req == SG_REQ_WRITE;
-  // MINB (minimum resident blocks per SM, i.e. a register cap) applies to the PLAIN instances only
-  if (a.wsum) return plain ? launch_fast<LPR, NV, UNROLL, 1, true, true, MINB>(a, K, n_items_cap, n_long_cap, st)
+  if (a.wsum) return plain ? launch_fast<LPR, NV, UNROLL, 1, true, true>(a, K, n_items_cap, n_long_cap, st)
                            : launch_fast<LPR, NV, UNROLL, 1, true>(a, K, n_items_cap, n_long_cap, st);
-  return plain ? launch_fast<LPR, NV, UNROLL, 1, false, true, MINB>(a, K, n_items_cap, n_long_cap, st)
+  return plain ? launch_fast<LPR, NV, UNROLL, 1, false, true>(a, K, n_items_cap, n_long_cap, st)
                : launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
 }
 
@@ -822,27 +542,8 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
         if (gather_shape() == 1) return dispatch_fast_mode<8, 2, 4>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 2) return dispatch_fast_mode<8, 2, 8>(a, K, n_items_cap, n_long_cap, st);
         if (gather_shape() == 3) return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 4) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 5) return dispatch_coop_mode<16, 8>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 7 || gather_shape() == 9) {  // software-pipelined on the short-segment launches only
-          if (nnz < 16LL * n_items_cap)
-            return gather_shape() == 7 ? dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st)
-                                       : dispatch_pipe_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
-          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
-        }
-        if (gather_shape() == 11 || gather_shape() == 12) {  // register cap: 8 (7) resident blocks per SM
-          if (nnz < 16LL * n_items_cap) return dispatch_fast_mode<16, 1, 4, 8>(a, K, n_items_cap, n_long_cap, st);
-          if (gather_shape() == 12) return dispatch_fast_mode<16, 1, 8, 7>(a, K, n_items_cap, n_long_cap, st);
-          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
-        }
-        if (gather_shape() == 8) return dispatch_pipe_mode<16, 3>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 10) return dispatch_pipe_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 6) {  // cooperative on the short-segment launches only
-          if (nnz < 16LL * n_items_cap) return dispatch_coop_mode<16, 4>(a, K, n_items_cap, n_long_cap, st);
-          return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
-        }
         // short segments (fewer than 16 edges per work item on average, the user side of a rating graph):
-        // batches of 4 waste fewer predicated tail slots than batches of 8 (0.303 -> 0.292 ms)
+        // batches of 4 — as fast as batches of 8 there (0.263 ms both) with 46 instead of 64 registers
         if (nnz < 16LL * n_items_cap) return dispatch_fast_mode<16, 1, 4>(a, K, n_items_cap, n_long_cap, st);
         return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
       case 128: return dispatch_fast_mode<32, 1, 8>(a, K, n_items_cap, n_long_cap, st);

@@ -1,5 +1,5 @@
 """Developer tool: time the four gather launches of one ML-10M-shaped step under tuning knobs, in one process.
-    python tools/sweep_gather.py "SG_GATHER_SHAPE=0" "SG_GATHER_SHAPE=11,SG_GATHER_GRID=8" ...
+    python tools/sweep_gather.py "SG_GATHER_SHAPE=0" "SG_GATHER_SHAPE=3,SG_GATHER_GRID=24" ...
 Each argument is a comma-separated list of NAME=VALUE environment settings (read by gather.cu on every call)."""
 import ctypes
 import os
