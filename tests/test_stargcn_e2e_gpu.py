@@ -1,4 +1,4 @@
-"""BASELINE.json config[1]: ML-100k-shaped transductive full STAR-GCN — two stacked encoder blocks, masked
+"""BASELINE.json configs[1] and [4]: ML-100k-shaped transductive and Douban-shaped inductive (user cold-start) full STAR-GCN — two stacked encoder blocks, masked
 input embeddings, reconstruction decoder and rating head, D=64 — assembled by stargcn_b200.model.StarGCN,
 against a torch-CPU fp64 execution of the SAME plans with plain dense/index ops in the reference's operator
 order (per level FullyConnected, weighted segment sum, add_n, LeakyReLU; Dense; take; losses).
@@ -80,12 +80,20 @@ def oracle(model, plans, lookups, needed, noise, recon_ids, gt_ratings, act, lam
     return float(loss), {n: (p.grad.double() if p.grad is not None else None) for n, p in P.items()}
 
 
-@pytest.mark.parametrize("act", ["identity", "leaky"])
-def test_full_stargcn_two_blocks_with_reconstruction(act):
+# (shape, setting): BASELINE.json configs[1] = ML-100k transductive; configs[4] = Douban-shaped inductive user
+# cold-start — 20 % of the users never show their own embedding (noise = -1 -> zero vector, as the reference feeds
+# held-out users, datasets.py:174-214 / iterators.py:329-351) and are the nodes to reconstruct.
+SETTINGS = [("ml-100k", "transductive", "identity"), ("ml-100k", "transductive", "leaky"),
+            ("douban", "inductive", "leaky")]
+
+
+@pytest.mark.parametrize("shape,setting,act", SETTINGS)
+def test_full_stargcn_two_blocks_with_reconstruction(shape, setting, act):
     from stargcn_b200 import synth
     from stargcn_b200.model import StarGCN
     from stargcn_b200.optim import FusedAdam
-    n_user, n_item, n_edges, _, _ = synth.SHAPES["ml-100k"]
+    n_user, n_item, n_edges, n_levels, _ = synth.SHAPES[shape]
+    assert n_levels == R
     g = synth.make_bipartite(n_user, n_item, n_edges, R, seed=1000)
     graph = from_synth(g)
     rs = np.random.RandomState(0)
@@ -97,10 +105,15 @@ def test_full_stargcn_two_blocks_with_reconstruction(act):
     for key, n in (("user", n_user), ("item", n_item)):
         nz = np.arange(n, dtype=np.int32)
         perm = rs.permutation(n)
-        n_rec = n // 10
-        recon[key] = perm[:n_rec].astype(np.int32)
-        nz[perm[: n_rec // 2]] = -1                                   # masked to zero
-        nz[perm[n_rec // 2: n_rec]] = rs.randint(0, n, n_rec - n_rec // 2)   # replaced by another node
+        if setting == "inductive" and key == "user":
+            n_rec = n // 5
+            recon[key] = perm[:n_rec].astype(np.int32)
+            nz[perm[:n_rec]] = -1                                         # cold-start users: always the zero vector
+        else:
+            n_rec = n // 10
+            recon[key] = perm[:n_rec].astype(np.int32)
+            nz[perm[: n_rec // 2]] = -1                                   # masked to zero
+            nz[perm[n_rec // 2: n_rec]] = rs.randint(0, n, n_rec - n_rec // 2)   # replaced by another node
         noise[key] = nz
     torch.manual_seed(0)
     mls = {("user", "item"): R, ("item", "user"): R}
