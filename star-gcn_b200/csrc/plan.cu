@@ -136,47 +136,146 @@ __device__ __forceinline__ int seg_of_pos(const int32_t *__restrict__ indptr, in
   return lo;
 }
 
+// A block owns a tile of kSegTile consecutive positions: two global searches find the first and last
+// segment that overlap it, their indptr entries are staged in shared memory, and every position then
+// searches that window (<= 12 steps in shared memory instead of ~20 dependent global loads: 92 -> ~20 us for
+// 8 M positions over 700 k segments).  A window wider than the staging buffer (long runs of empty segments)
+// falls back to the global search.  Same result as one seg_of_pos per position.
+constexpr int kSegTile = 2048;
+constexpr int kSegWin = 2560;  // staged indptr entries
+
 __global__ void __launch_bounds__(256) seg_ids_kernel(int32_t *__restrict__ seg_ids,
                                                       const int32_t *__restrict__ indptr, int n_seg, int nnz) {
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x)
-    seg_ids[p] = seg_of_pos(indptr, n_seg, p);
+  __shared__ int32_t s_ptr[kSegWin];
+  __shared__ int s_lohi[2];
+  const int n_tiles = ceil_div(nnz, kSegTile);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int p0 = tile * kSegTile, p1 = min(p0 + kSegTile, nnz);
+    if (threadIdx.x == 0) s_lohi[0] = seg_of_pos(indptr, n_seg, p0);
+    if (threadIdx.x == 32) s_lohi[1] = seg_of_pos(indptr, n_seg, p1 - 1);
+    __syncthreads();
+    const int lo = s_lohi[0], cnt = s_lohi[1] - lo + 1;  // segments lo .. lo + cnt - 1 overlap the tile
+    const bool staged = cnt + 1 <= kSegWin;
+    if (staged)
+      for (int i = threadIdx.x; i <= cnt; i += blockDim.x) s_ptr[i] = __ldg(indptr + lo + i);
+    __syncthreads();
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      int seg;
+      if (staged) {
+        int l = 0, h = cnt - 1;  // first j with s_ptr[j + 1] > p; j = cnt - 1 always qualifies
+        while (l < h) {
+          const int m = (l + h) >> 1;
+          if (s_ptr[m + 1] > p) h = m; else l = m + 1;
+        }
+        seg = lo + l;
+      } else {
+        seg = seg_of_pos(indptr, n_seg, p);
+      }
+      seg_ids[p] = seg;
+    }
+    __syncthreads();  // the next tile overwrites the window
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// plan build
+// plan build in three launches: per-tile sums of (items, long segments, partial slots) straight from
+// indptr, one single-block scan of the tile sums (three channels), and a fill pass that redoes the block
+// scan and writes the work items.  (The first version materialised three count arrays and ran a
+// 3-launch scan on each: 11 launches per schedule, two schedules per plan, rebuilt with every plan.)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) plan_count(const int32_t *__restrict__ indptr, int n_seg, int chunk,
-                                                  int32_t *__restrict__ c_item, int32_t *__restrict__ c_long,
-                                                  int32_t *__restrict__ c_part) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_seg) return;
-  int len = indptr[s + 1] - indptr[s];
-  int nch = len <= chunk ? 1 : ceil_div(len, chunk);
-  c_item[s] = nch;
-  c_long[s] = len > chunk;
-  c_part[s] = len > chunk ? nch : 0;
+__device__ __forceinline__ void plan_counts(int len, int chunk, int &n_item, int &n_long, int &n_part) {
+  const bool is_long = len > chunk;
+  n_item = is_long ? ceil_div(len, chunk) : 1;
+  n_long = is_long ? 1 : 0;
+  n_part = is_long ? n_item : 0;
 }
 
-__global__ void __launch_bounds__(256) plan_fill(PlanHeader *hdr, int4 *__restrict__ items, int4 *__restrict__ longs,
-                                                 const int32_t *__restrict__ indptr, int n_seg, int nnz, int chunk,
-                                                 const int32_t *__restrict__ o_item, const int32_t *__restrict__ o_long,
-                                                 const int32_t *__restrict__ o_part, int cap_items, int cap_long) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) {
+__global__ void __launch_bounds__(kScanThreads) plan_tile_sums(const int32_t *__restrict__ indptr, int n_seg, int chunk,
+                                                               int32_t *__restrict__ tile_sums, int n_tiles) {
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  int s_item = 0, s_long = 0, s_part = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) {
+    const int s = base + i;
+    if (s < n_seg) {
+      int a, b, c;
+      plan_counts(__ldg(indptr + s + 1) - __ldg(indptr + s), chunk, a, b, c);
+      s_item += a; s_long += b; s_part += c;
+    }
+  }
+  int t_item, t_long, t_part;
+  block_incl_scan(s_item, &t_item);
+  block_incl_scan(s_long, &t_long);
+  block_incl_scan(s_part, &t_part);
+  if (threadIdx.x == 0) {
+    tile_sums[blockIdx.x] = t_item;
+    tile_sums[n_tiles + blockIdx.x] = t_long;
+    tile_sums[2 * n_tiles + blockIdx.x] = t_part;
+  }
+}
+
+// exclusive scan of the three channels of tile sums in place; totals -> hdr->n_items / n_long / n_partials
+__global__ void __launch_bounds__(kScanThreads) plan_scan_tiles(int32_t *tile_sums, int n_tiles, PlanHeader *hdr) {
+  for (int ch = 0; ch < 3; ++ch) {
+    int32_t *t = tile_sums + ch * n_tiles;
+    int carry = 0;
+    for (int base = 0; base < n_tiles; base += kScanThreads) {
+      const int i = base + threadIdx.x;
+      const int v = i < n_tiles ? t[i] : 0;
+      int total;
+      const int inc = block_incl_scan(v, &total);
+      if (i < n_tiles) t[i] = carry + inc - v;
+      carry += total;
+    }
+    if (threadIdx.x == 0) {
+      if (ch == 0) hdr->n_items = carry;
+      else if (ch == 1) hdr->n_long = carry;
+      else hdr->n_partials = carry;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_fill_fused(PlanHeader *hdr, int4 *__restrict__ items, int4 *__restrict__ longs,
+                                                                const int32_t *__restrict__ indptr, int n_seg, int nnz, int chunk,
+                                                                const int32_t *__restrict__ tile_offs, int n_tiles,
+                                                                int cap_items, int cap_long) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     hdr->chunk = chunk; hdr->n_seg = n_seg; hdr->nnz = nnz; hdr->cap_items = cap_items; hdr->cap_long = cap_long;
   }
-  if (s >= n_seg) return;
-  const int beg = indptr[s], end = indptr[s + 1], len = end - beg;
-  const int base = o_item[s];
-  if (len <= chunk) {
-    items[base] = make_int4(beg, end, s, -1);
-  } else {
-    const int nch = ceil_div(len, chunk), slot = o_part[s];
-    for (int c = 0; c < nch; ++c) {
-      int b = beg + c * chunk;
-      items[base + c] = make_int4(b, min(b + chunk, end), s, slot + c);
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  int beg[kScanPerThread + 1];
+#pragma unroll
+  for (int i = 0; i <= kScanPerThread; ++i) beg[i] = base + i <= n_seg ? __ldg(indptr + base + i) : 0;
+  int s_item = 0, s_long = 0, s_part = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) {
+    if (base + i < n_seg) {
+      int a, b, c;
+      plan_counts(beg[i + 1] - beg[i], chunk, a, b, c);
+      s_item += a; s_long += b; s_part += c;
     }
-    longs[o_long[s]] = make_int4(s, slot, nch, 0);
+  }
+  int total;
+  int o_item = block_incl_scan(s_item, &total) - s_item + tile_offs[blockIdx.x];
+  int o_long = block_incl_scan(s_long, &total) - s_long + tile_offs[n_tiles + blockIdx.x];
+  int o_part = block_incl_scan(s_part, &total) - s_part + tile_offs[2 * n_tiles + blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) {
+    const int s = base + i;
+    if (s >= n_seg) break;
+    const int b0 = beg[i], e0 = beg[i + 1], len = e0 - b0;
+    if (len <= chunk) {
+      items[o_item] = make_int4(b0, e0, s, -1);
+      o_item += 1;
+    } else {
+      const int nch = ceil_div(len, chunk);
+      for (int c = 0; c < nch; ++c) {
+        const int b = b0 + c * chunk;
+        items[o_item + c] = make_int4(b, min(b + chunk, e0), s, o_part + c);
+      }
+      longs[o_long] = make_int4(s, o_part, nch, 0);
+      o_item += nch; o_long += 1; o_part += nch;
+    }
   }
 }
 
@@ -269,6 +368,12 @@ static inline int grid_for(long long n, int threads = 256) {
   return (int)(g < cap ? g : cap);
 }
 
+static inline int seg_ids_grid(int nnz) {  // one block per tile of positions, grid-stride beyond 32 blocks per SM
+  const long long tiles = ceil_div<long long>(nnz > 0 ? nnz : 1, kSegTile);
+  const long long cap = (long long)num_sms() * 32;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
 static int key_bits(int n_nb) {
   int bits = 1;
   while (bits < 31 && (1LL << bits) < (long long)n_nb) ++bits;
@@ -290,7 +395,7 @@ int sg_seg_ids(int32_t *seg_ids, const int32_t *indptr, int n_seg, int nnz, sg_s
   SG_REQUIRE(n_seg >= 0 && nnz >= 0, "sg_seg_ids: negative size (n_seg=%d nnz=%d)", n_seg, nnz);
   if (nnz == 0) return SG_OK;
   SG_REQUIRE(seg_ids && indptr, "sg_seg_ids: null pointer");
-  seg_ids_kernel<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(seg_ids, indptr, n_seg, nnz);
+  seg_ids_kernel<<<seg_ids_grid(nnz), 256, 0, (cudaStream_t)stream>>>(seg_ids, indptr, n_seg, nnz);
   SG_LAUNCHED("seg_ids_kernel");
   return SG_OK;
 }
@@ -335,7 +440,7 @@ int sg_csr_transpose(int32_t *t_indptr, int32_t *t_perm, int32_t *t_seg, const i
 
   iota_kernel<<<grid_for(nnz), 256, 0, st>>>(iota, nnz);
   SG_LAUNCHED("iota_kernel");
-  seg_ids_kernel<<<grid_for(nnz), 256, 0, st>>>(seg_ids, indptr, n_seg, nnz);
+  seg_ids_kernel<<<seg_ids_grid(nnz), 256, 0, st>>>(seg_ids, indptr, n_seg, nnz);
   SG_LAUNCHED("seg_ids_kernel");
   // LSD radix sort is stable: equal destinations keep ascending original position.
   SG_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, indices, keys_sorted, (const int32_t *)iota, t_perm, nnz,
@@ -381,16 +486,17 @@ int sg_plan_build(void *plan, size_t plan_bytes, const int32_t *indptr, int n_se
   void *scan_ws = scan_base + 3 * arr;
   SG_CUDA(cudaMemsetAsync(hdr, 0, sizeof(PlanHeader), st));
   if (n_seg == 0) return SG_OK;
-  const int g = ceil_div(n_seg, 256);
-  plan_count<<<g, 256, 0, st>>>(indptr, n_seg, chunk, a_item, a_long, a_part);
-  SG_LAUNCHED("plan_count");
-  int rc;
-  if ((rc = exclusive_scan_i32(a_item, a_item, n_seg, &hdr->n_items, scan_ws, st)) != SG_OK) return rc;
-  if ((rc = exclusive_scan_i32(a_long, a_long, n_seg, &hdr->n_long, scan_ws, st)) != SG_OK) return rc;
-  if ((rc = exclusive_scan_i32(a_part, a_part, n_seg, &hdr->n_partials, scan_ws, st)) != SG_OK) return rc;
-  plan_fill<<<g, 256, 0, st>>>(hdr, items, longs, indptr, n_seg, nnz, chunk, a_item, a_long, a_part,
-                               (int)plan_cap_items(n_seg, nnz, chunk), (int)plan_cap_long(nnz, chunk));
-  SG_LAUNCHED("plan_fill");
+  // the scan region (3 count arrays + scan scratch in the first version) now only holds 3 x n_tiles tile sums
+  (void)a_long; (void)a_part; (void)scan_ws;
+  const int n_tiles = ceil_div(n_seg, kScanTile);
+  int32_t *tile_sums = a_item;
+  plan_tile_sums<<<n_tiles, kScanThreads, 0, st>>>(indptr, n_seg, chunk, tile_sums, n_tiles);
+  SG_LAUNCHED("plan_tile_sums");
+  plan_scan_tiles<<<1, kScanThreads, 0, st>>>(tile_sums, n_tiles, hdr);
+  SG_LAUNCHED("plan_scan_tiles");
+  plan_fill_fused<<<n_tiles, kScanThreads, 0, st>>>(hdr, items, longs, indptr, n_seg, nnz, chunk, tile_sums, n_tiles,
+                                                    (int)plan_cap_items(n_seg, nnz, chunk), (int)plan_cap_long(nnz, chunk));
+  SG_LAUNCHED("plan_fill_fused");
   return SG_OK;
 }
 
