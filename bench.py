@@ -43,6 +43,17 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--sampled", type=int, default=0, metavar="K",
                     help="N=1 only: build the layer inputs with the DEVICE sampler at fan-out K (0 = full neighbourhood lists)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every rank owns an ML-10M-shaped slice of an N-times larger graph (default); "
+                         "strong = the ML-10M graph itself, node ranges balanced by nnz (SURVEY 8e)")
+    ap.add_argument("--halo-mode", default="auto", choices=["auto", "alltoall", "allgather"],
+                    help="N>1: force the halo exchange (auto picks all-gather / reduce-scatter when the halo is dense)")
+    ap.add_argument("--check", action="store_true",
+                    help="N>1: run the partitioned step over NCCL in both exchange modes (and on the strong partition) on a "
+                         "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")
+    ap.add_argument("--presplit", action="store_true", help="A/B: round-1 GEMM path (operands pre-split in HBM)")
+    ap.add_argument("--dev", action="append", default=[], metavar="NAME=VALUE",
+                    help="development option of the library (sg_dev_option), e.g. gather_variant=1")
     return ap.parse_args()
 
 
@@ -288,6 +299,150 @@ def run_cpu_arm(wl, steps, warmup, budget_s):
 
 
 # ------------------------------------------------------------------------------------------------
+# node partitions (N > 1)
+# ------------------------------------------------------------------------------------------------
+def partition_sides(base, rank, world, scaling):
+    """Per layer direction what this rank owns: (indptr, global column ids, rating values, support) of ITS destination
+    rows, the ownership ranges of the neighbour type, and the number of destination rows.
+      weak    every rank owns a base-shaped slice of a world-times larger graph (dist.partitioned_layer_inputs)
+      strong  the base graph itself: contiguous user / item ranges balanced by nnz (dist.balanced_ranges), SURVEY 8e"""
+    from stargcn_b200 import dist as sgd
+    if scaling == "weak":
+        part = sgd.partitioned_layer_inputs(base, rank, world)
+        return {"user": dict(csr=part["user"], nb_ranges=part["item_ranges"], n_dst=base["n_user"], dst_lo=rank * base["n_user"]),
+                "item": dict(csr=part["item"], nb_ranges=part["user_ranges"], n_dst=base["n_item"], dst_lo=rank * base["n_item"])}
+    u_ranges = sgd.balanced_ranges(np.diff(base["u2i"]["indptr"].astype(np.int64)), world)
+    i_ranges = sgd.balanced_ranges(np.diff(base["i2u"]["indptr"].astype(np.int64)), world)
+    out = {}
+    for side, key, own, nb in (("user", "u2i", u_ranges, i_ranges), ("item", "i2u", i_ranges, u_ranges)):
+        c = base[key]
+        lo, hi = int(own[rank]), int(own[rank + 1])
+        p0, p1 = int(c["indptr"][lo]), int(c["indptr"][hi])
+        indptr = (c["indptr"][lo:hi + 1].astype(np.int64) - p0).astype(np.int32)
+        out[side] = dict(csr=(indptr, c["cols"][p0:p1].astype(np.int64), c["vals"][p0:p1], c["support"][p0:p1]),
+                         nb_ranges=nb, n_dst=hi - lo, dst_lo=lo)
+    return out
+
+
+def run_check(args, rank, world, local_rank):
+    """Partitioned step over NCCL vs the same layer on the whole graph (rank 0), both exchange modes on the weak
+    construction and the nnz-balanced strong partition: forward rows, the data gradient of the rank's own feature
+    rows (includes the halo gradients its peers return) and the all-reduced weight / bias gradients, at 1e-5."""
+    import torch
+    import torch.distributed as dist
+    import stargcn_b200  # noqa: F401
+    from stargcn_b200 import dist as sgd, synth
+    from stargcn_b200.graph import MultiLinkCSR
+    from stargcn_b200.layers import MultiLinkGCNAggregator
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    R, D, U = 5, 64, AGG_UNITS
+    base = synth.make_bipartite(3000, 2000, 90_000, n_levels=R, seed=3)
+    ws, bs = make_params(R, D, U, seed=11)
+    bs = [np.random.RandomState(20 + r).uniform(-0.2, 0.2, U).astype(np.float32) for r in range(R)]
+
+    def make_agg():
+        agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", ordinal_sharing=False, accum="sum", in_units=D).to(dev)
+        with torch.no_grad():
+            for i in range(R):
+                getattr(agg, f"weight{i}").copy_(torch.from_numpy(ws[i]))
+                getattr(agg, f"bias{i}").copy_(torch.from_numpy(bs[i]))
+        return agg
+
+    def rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+    report, ok = {}, True
+    for scaling, mode in (("weak", "alltoall"), ("weak", "allgather"), ("strong", "alltoall")):
+        sides = partition_sides(base, rank, world, scaling)
+        s = sides["user"]
+        indptr, cols, vals, sup = s["csr"]
+        n_nb_total = int(s["nb_ranges"][-1])
+        n_dst_total = world * base["n_user"] if scaling == "weak" else base["n_user"]
+        rs = np.random.RandomState(5)
+        x_all = rs.normal(size=(n_nb_total, D)).astype(np.float32)
+        gout_all = rs.normal(size=(n_dst_total, U)).astype(np.float32)
+        plan = sgd.HaloPlan(cols, s["nb_ranges"], rank, world, index_device=dev, mode=mode).to(dev)
+        lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, base["levels"])[:3]
+        csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev)
+        lo, hi = int(s["nb_ranges"][rank]), int(s["nb_ranges"][rank + 1])
+        x_local = torch.from_numpy(x_all[lo:hi]).to(dev).requires_grad_(True)
+        agg = make_agg()
+        out = agg(sgd.halo_exchange(x_local, plan), csr)
+        out.backward(torch.from_numpy(gout_all[s["dst_lo"]:s["dst_lo"] + s["n_dst"]]).to(dev))
+        sgd.allreduce_grads(list(agg.parameters()))
+        mine = dict(out=out.detach().cpu().numpy(), gx=x_local.grad.cpu().numpy(), gw=agg.weight2.grad.cpu().numpy(),
+                    gb=agg.bias2.grad.cpu().numpy(), dst_lo=s["dst_lo"], nb_lo=lo, n_halo=plan.n_halo, mode=plan.mode,
+                    csr=(indptr, cols, vals, sup))
+        got = [None] * world
+        dist.all_gather_object(got, mine)
+        if rank == 0:
+            order = np.argsort([g["dst_lo"] for g in got])
+            indptr_g = np.concatenate([[0]] + [np.diff(got[k]["csr"][0].astype(np.int64)) for k in order]).cumsum().astype(np.int32)
+            cols_g = np.concatenate([got[k]["csr"][1] for k in order]).astype(np.int32)
+            vals_g = np.concatenate([got[k]["csr"][2] for k in order])
+            sup_g = np.concatenate([got[k]["csr"][3] for k in order])
+            whole = MultiLinkCSR(*synth.split_by_level(indptr_g, cols_g, vals_g, sup_g, base["levels"])[:3], n_nb=n_nb_total, device=dev)
+            agg0 = make_agg()
+            xg = torch.from_numpy(x_all).to(dev).requires_grad_(True)
+            o = agg0(xg, whole)
+            o.backward(torch.from_numpy(gout_all).to(dev))
+            o_h, gx_h = o.detach().cpu().numpy(), xg.grad.cpu().numpy()
+            errs = dict(out=0.0, gx=0.0, gw=0.0, gb=0.0)
+            for g in got:
+                errs["out"] = max(errs["out"], rel(g["out"], o_h[g["dst_lo"]:g["dst_lo"] + g["out"].shape[0]]))
+                errs["gx"] = max(errs["gx"], rel(g["gx"], gx_h[g["nb_lo"]:g["nb_lo"] + g["gx"].shape[0]]))
+                errs["gw"] = max(errs["gw"], rel(g["gw"], agg0.weight2.grad.cpu().numpy()))
+                errs["gb"] = max(errs["gb"], rel(g["gb"], agg0.bias2.grad.cpu().numpy()))
+            errs["halo_rows"] = [int(g["n_halo"]) for g in got]
+            errs["mode_used"] = got[0]["mode"]
+            errs["ok"] = bool(max(errs["out"], errs["gx"], errs["gw"], errs["gb"]) <= 1e-5 and all(h > 0 for h in errs["halo_rows"]))
+            ok = ok and errs["ok"]
+            report[f"{scaling}/{mode}"] = errs
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    if rank == 0:
+        print(json.dumps(dict(check="partitioned step over NCCL vs whole graph", n_gpus=world, tolerance=1e-5,
+                              ok=bool(flag.item()), cases=report)))
+    return 0 if int(flag.item()) else 1
+
+
+def probe_row_gather(dev, table_bytes_list, blocks=None):
+    """Measured ceiling of a random 256-byte-row gather (sg_row_gather_probe, csrc/probe.cu) for tables of the given
+    sizes: GB/s of row bytes, best of 5 after warm-up.  Outside every timed region."""
+    import ctypes
+    import torch
+    from stargcn_b200 import _lib
+    from stargcn_b200._lib import check
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks = blocks or sms * 32
+    reads = 256
+    out = torch.empty((blocks * 16, 64), device=dev)
+    res = {}
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for nbytes in table_bytes_list:
+        n_rows = max(int(nbytes) // 256, 1)
+        table = torch.randn((n_rows, 64), device=dev)
+        best = None
+        for it in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.sg_row_gather_probe(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(table.data_ptr()), n_rows, reads,
+                                          blocks, 17 + it, st), "sg_row_gather_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if it >= 3:
+                best = ms if best is None else min(best, ms)
+        res[int(nbytes)] = blocks * 16 * reads * 256 / (best * 1e-3) / 1e9
+        del table
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu_arm(args, rank, world, local_rank):
@@ -300,6 +455,11 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.presplit:
+        graph.GEMM_INKERNEL_SPLIT = False
+    for kv in args.dev:
+        name, _, val = kv.partition("=")
+        _lib.dev_option(name, int(val))
     if world > 1:
         if rank == 0:
             load_base(args.workload)      # generate + cache once; the other ranks read the cache
@@ -342,21 +502,24 @@ def run_gpu_arm(args, rank, world, local_rank):
             csr = MultiLinkCSR(*wl[side], n_nb=x_nb.shape[0], device=dev).prepare(backward=True)
             sides[side] = dict(csr=csr, x_np=x_nb, n_dst=n_dst, plan=None)
     else:
-        # node-partitioned path: this rank owns an ML-10M-shaped slice of a world-times larger graph and
-        # fetches the neighbour rows it does not own with one all-to-all per layer direction
+        # node-partitioned path: the rank owns the destination rows of its node ranges and fetches the neighbour rows
+        # it does not own with one exchange per layer direction (weak: an ML-10M-shaped slice of a world-times larger
+        # graph per rank; strong: the ML-10M graph itself cut into nnz-balanced ranges)
         from stargcn_b200 import dist as sgd, synth
-        part = sgd.partitioned_layer_inputs(wl["base"], rank, world)
+        part = partition_sides(wl["base"], rank, world, args.scaling)
         rng = np.random.default_rng(2000 + rank)
-        for side, nb_ranges, n_dst in (("user", part["item_ranges"], wl["n_user"]), ("item", part["user_ranges"], wl["n_item"])):
-            indptr, cols, vals, sup = part[side]
+        for side in ("user", "item"):
+            ps = part[side]
+            indptr, cols, vals, sup = ps["csr"]
             # one communicator per direction: their collectives then run on independent NCCL streams and one
             # direction's exchange overlaps the other direction's compute instead of queueing behind it
             side_group = dist.new_group(backend="nccl")
-            plan = sgd.HaloPlan(cols, nb_ranges, rank, world, group=side_group, index_device=dev).to(dev)
+            plan = sgd.HaloPlan(cols, ps["nb_ranges"], rank, world, group=side_group, index_device=dev,
+                                mode=args.halo_mode).to(dev)
             lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, wl["base"]["levels"])[:3]
             csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev).prepare(backward=True)
             x_np = rng.standard_normal((plan.n_local, D), dtype=np.float32)
-            sides[side] = dict(csr=csr, x_np=x_np, n_dst=n_dst, plan=plan)
+            sides[side] = dict(csr=csr, x_np=x_np, n_dst=ps["n_dst"], plan=plan)
     for side, s_ in sides.items():
         agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", dropout_rate=0.0, ordinal_sharing=False,
                                      accum="sum", in_units=D).to(dev)
@@ -464,7 +627,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     ms_per_step = ms_total / args.steps
     value = total_edges / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (gather_rows_kernel), from events on its own stream ----
+    # ---- roofline of the dominant kernel (the gather, 4 launches per step), from events on its own stream ----
+    # Three denominators, each stated: (1) bound "l2": the MEASURED ceiling of a random 256-byte-row gather on a table
+    # of the size each launch reads (probe_row_gather; the tables are 2.7 - 27 MB and live in the 126 MB L2, one source
+    # of 179 MB does not); (2) hbm_compulsory_frac: bytes that must cross HBM at least once / time / measured HBM copy
+    # peak; (3) dram_frac: ncu-measured DRAM bytes of the same launches (profiles/traffic.json) / time / HBM peak.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -482,7 +649,11 @@ def run_gpu_arm(args, rank, world, local_rank):
             continue
         fwd = tag == "agg_fwd"
         by = algorithmic_bytes(csr.nnz, csr.n_seg, csr.n_nb, D, fwd)
-        d = detail.setdefault(key, dict(ms=0.0, n=0, bytes=by, edges=csr.nnz))
+        # gathered table and compulsory HBM bytes of this launch: forward reads x [n_nb, D] and writes [n_dst, R*D (+R)];
+        # the transposed launch reads gagg [n_dst, R*D] and writes gx [n_nb, D]; both stream index + weight once
+        table = csr.n_nb * D * 4 if fwd else csr.n_dst * R * D * 4
+        comp = 8 * csr.nnz + 4 * csr.n_seg + 4 * D * csr.n_nb + 4 * R * D * csr.n_dst
+        d = detail.setdefault(key, dict(ms=0.0, n=0, bytes=by, edges=csr.nnz, table_bytes=table, compulsory_bytes=comp))
         d["ms"] += a.elapsed_time(b); d["n"] += 1
     gemm_ms, gemm_flops = 0.0, 0.0
     for key, d in gemm.items():
@@ -490,27 +661,52 @@ def run_gpu_arm(args, rank, world, local_rank):
         d["tflops_fp32_equiv"] = d["flops"] / (d["ms"] * 1e-3) / 1e12     # algorithmic 2MNK
         d["tflops_tf32_issued"] = 3 * d["tflops_fp32_equiv"]                # three TF32 products per fp32 product
         gemm_ms += d["ms"]; gemm_flops += d["flops"]
+    probe = {}
+    try:
+        probe = probe_row_gather(dev, sorted({d["table_bytes"] for d in detail.values()}))
+    except Exception as e:
+        print(f"[bench] row-gather probe failed: {e}", file=sys.stderr)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    ideal_ms, comp_bytes = 0.0, 0.0
     for key, d in detail.items():
         d["ms"] /= max(d["n"], 1)
         d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        d["frac"] = d["gbs"] / peak_gbs
         d["gedges_s"] = d["edges"] / (d["ms"] * 1e-3) / 1e9
-        tot_bytes += d["bytes"]; tot_ms += d["ms"]
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gather_rows_kernel_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel="gather_rows_kernel (4 launches/step)", achieved=tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms else None,
-                    peak=peak_gbs, peak_source=peak_src, unit="GB/s", frac=(tot_bytes / (tot_ms * 1e-3) / 1e9 / peak_gbs) if tot_ms else None,
-                    traffic=traffic, share_of_step=tot_ms / ms_per_step if ms_per_step else None,
+        d["hbm_model_frac"] = d["gbs"] / peak_gbs                          # gather-model bytes vs the HBM copy peak (> 1: L2-served)
+        d["hbm_compulsory_frac"] = d["compulsory_bytes"] / (d["ms"] * 1e-3) / 1e9 / peak_gbs
+        pk = probe.get(int(d["table_bytes"]))
+        if pk:
+            d["l2_probe_gbs"] = pk
+            d["frac"] = d["gbs"] / pk
+            ideal_ms += d["bytes"] / (pk * 1e9) * 1e3
+        tot_bytes += d["bytes"]; tot_ms += d["ms"]; comp_bytes += d["compulsory_bytes"]
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms else None
+    l2_peak = tot_bytes / (ideal_ms * 1e-3) / 1e9 if ideal_ms else None       # time-weighted probe rate of the four tables
+    dram_per_launch = (traffic or {}).get("gather_rows_kernel_bytes_per_launch")
+    roofline = dict(bound="l2" if l2_peak else "hbm", kernel="gather_rows_fast_kernel (4 launches/step)", achieved=achieved,
+                    peak=l2_peak if l2_peak else peak_gbs,
+                    peak_source="measured in this run: sg_row_gather_probe (random 256-B rows, no index dependence) on tables "
+                                "of the four launches' sizes, combined by bytes" if l2_peak else peak_src,
+                    unit="GB/s", frac=(achieved / l2_peak) if l2_peak else (achieved / peak_gbs if achieved else None),
+                    hbm_peak=peak_gbs, hbm_peak_source=peak_src,
+                    hbm_model_frac=achieved / peak_gbs if achieved else None,
+                    hbm_compulsory_frac=(comp_bytes / (tot_ms * 1e-3) / 1e9 / peak_gbs) if tot_ms else None,
+                    dram_frac=(dram_per_launch * len(detail) / (tot_ms * 1e-3) / 1e9 / peak_gbs) if (dram_per_launch and tot_ms) else None,
+                    traffic=dram_per_launch, share_of_step=tot_ms / ms_per_step if ms_per_step else None,
                     per_launch={k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in detail.items()})
     transform = None
     if gemm:
-        transform = dict(kernel="tf32x3_gemm_kernel (tcgen05 3xTF32, 6 launches/step)", bound="tensor", ms_per_step=gemm_ms,
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0   # no TF32 peak is measured: half the measured bf16 burst
+        transform = dict(kernel="tf32x3_gemm_split_kernel / _pair_kernel (tcgen05 3xTF32, 6 launches/step)", bound="tensor", ms_per_step=gemm_ms,
                          share_of_step=gemm_ms / ms_per_step if ms_per_step else None,
                          tflops_fp32_equiv=gemm_flops / (gemm_ms * 1e-3) / 1e12, tflops_tf32_issued=3 * gemm_flops / (gemm_ms * 1e-3) / 1e12,
-                         peak_tf32_nominal=1100.0, unit="TFLOP/s",
+                         peak=tf32_peak, peak_source="half of MEASURED_PEAKS bf16 burst (TF32 runs at half the bf16 rate)",
+                         frac=3 * gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf32_peak, unit="TFLOP/s",
+                         operands="plain fp32, split in the kernel" if graph.GEMM_INKERNEL_SPLIT else "pre-split in HBM",
                          per_launch={k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in gemm.items()})
 
     # ---- end to end through the public layer API with HOST buffers (H2D + D2H inside) ----
@@ -518,17 +714,28 @@ def run_gpu_arm(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_streams)
 
+    modes = {side: s_["plan"].mode for side, s_ in sides.items() if s_["plan"] is not None}
+    halo_by_side = {side: int(s_["plan"].n_halo) for side, s_ in sides.items() if s_["plan"] is not None}
+    if world == 1:
+        parallelism = "single GPU"
+    else:
+        what = (f"each rank owns an {args.workload}-shaped slice of a {world}x larger graph" if args.scaling == "weak" else
+                f"the {args.workload} graph itself cut into {world} contiguous node ranges per side, balanced by nnz")
+        coll = {"allgather": "NCCL all-gather of the neighbour-row blocks fwd + reduce-scatter bwd (dense halo: every rank needs "
+                             "nearly every remote row)",
+                "alltoall": "NCCL all-to-all(v) of deduplicated halo rows fwd + its transpose bwd"}
+        parallelism = (f"node-partitioned over {world} GPUs ({what}); per layer direction: " +
+                       "; ".join(f"{side} side: {coll[m]}, rank-0 halo {halo_by_side[side]} rows x {D * 4} B" for side, m in modes.items()) +
+                       "; all-reduce of the packed weight gradient inside the backward")
     result = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                  ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                  ms_per_step=ms_per_step, higher_is_better=True,
+                  scaling=args.scaling if world > 1 else "weak", vs_baseline=None, dtype="f32",
                   data="synthetic",
                   config=dict(workload=f"{args.workload}-shaped bipartite rating graph: {wl['n_user']} users x {wl['n_item']} items, "
                                        f"{wl['nnz']} edges/direction, R={R} levels, D={D}, agg units={U}; one HeterGCN layer, both "
                                        f"directions, fwd+bwd; full neighbourhood",
                               edges_per_step_per_gpu=edges_per_step,
-                              parallelism="single GPU" if world == 1 else
-                              f"node-partitioned over {world} GPUs (each rank owns an ML-10M-shaped slice of a {world}x larger graph); "
-                              f"per layer direction one NCCL all-to-all of halo rows fwd + its transpose bwd, all-reduce of weight grads; "
-                              f"rank 0 halo = {halo_rows} rows x {D * 4} B per step-direction pair",
+                              parallelism=parallelism,
                               total_edges_per_step=total_edges,
                               execution=("one CUDA graph per step (captured once, replayed K times): " if graphed else "eager launches: ") +
                               "the two directions on two streams",
@@ -536,6 +743,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                                   (sum(algorithmic_bytes(s['csr'].nnz, s['csr'].n_seg, s['csr'].n_nb, 0, True) for s in sides.values()) * 2
                                    + sum(s['n_dst'] * (R * D + U) * 4 * 3 for s in sides.values())) / 1e6)),
                   clocks=clocks, gpu_launches=int(launches), roofline=roofline)
+    if world == 1:
+        result["scaling_note"] = "single GPU: the N=1 point of the weak-scaling series (per-GPU work is what every rank gets at N>1)"
+    else:
+        result["collective"] = dict(mode=modes, halo_rows_rank0=halo_by_side)
     if transform is not None:
         result["transform_gemm"] = transform
     if sampler_info is not None:
@@ -547,11 +758,13 @@ def run_gpu_arm(args, rank, world, local_rank):
 
 
 def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_streams=None):
-    """Same step through the public API starting from PINNED HOST buffers: per step the CSR lists,
-    features and upstream gradient are copied host->device, the device plan (concatenated CSR, stable
-    transpose, schedules) is rebuilt — the reference re-uploads and re-sorts per call too
-    (layers.py:366-377, seg_op.cu:882-926) — forward + backward run (with the halo exchange and the
-    gradient all-reduce when partitioned), and a scalar read-back ends it."""
+    """Same step through the public API in the REFERENCE-SHAPED call: the caller holds, per direction, the three
+    per-level lists (end points, indptr, support) and the features in PINNED HOST memory — what gen_plan hands
+    heter_sage (layers.py:303-336, 366-377).  Per step: ``MultiLinkCSR(lists)`` copies every level straight into the
+    concatenated device arrays (asynchronously, on a copy stream one step ahead) and assembles the indptr on the
+    device, the device plan (stable transpose, schedules) is rebuilt — the reference re-uploads and re-sorts per
+    call too (seg_op.cu:882-926) — forward + backward run (with the halo exchange and the gradient all-reduce when
+    partitioned), and a scalar read-back ends it.  No device->host transfer other than that scalar."""
     import torch
     from stargcn_b200 import runtime
     from stargcn_b200.graph import MultiLinkCSR
@@ -562,36 +775,46 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
     h2d = 0
     for side in ("user", "item"):
         csr = sides[side]["csr"]
-        host[side] = dict(ep=csr.end_points.cpu().pin_memory(), sup=csr.support.cpu().pin_memory(),
-                          ptr=csr.cat_indptr.cpu().pin_memory(), x=torch.from_numpy(sides[side]["x_np"]).pin_memory())
-        h2d += sum(t.numel() * t.element_size() for t in host[side].values())
+        ep, sup, ptr = csr.end_points.cpu(), csr.support.cpu(), csr.cat_indptr.cpu().to(torch.int64)
+        n_dst = csr.n_dst
+        offs = [int(ptr[r * n_dst]) for r in range(R)] + [csr.nnz]
+        ep_l = [ep[offs[r]:offs[r + 1]].clone().pin_memory() for r in range(R)]
+        sup_l = [sup[offs[r]:offs[r + 1]].clone().pin_memory() for r in range(R)]
+        ptr_l = [(ptr[r * n_dst:(r + 1) * n_dst + 1] - offs[r]).to(torch.int32).pin_memory() for r in range(R)]
+        host[side] = dict(ep_l=ep_l, sup_l=sup_l, ptr_l=ptr_l, nnz_l=[offs[r + 1] - offs[r] for r in range(R)],
+                          x=torch.from_numpy(sides[side]["x_np"]).pin_memory())
+        h2d += sum(t.numel() * t.element_size() for t in ep_l + sup_l + ptr_l + [host[side]["x"]])
 
     # double-buffered prefetch: while step i computes, step i+1's inputs cross PCIe on a copy stream
     # (what a loader thread does); every step still copies all of its inputs inside the timed region
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = []
-    for _ in range(2):
-        slots.append({side: {k: torch.empty_like(t, device=dev) for k, t in host[side].items()} for side in host})
+    main = torch.cuda.current_stream()
+    consumers = [main] + list(side_streams or [])
+    slots = [None, None]
     ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
-    for ev in free:
-        ev.record()
 
     # per-resource breakdown (reported, not part of the metric): event pairs around the copies on the copy
     # stream and around the compute on the main stream, read after the timed region
     copy_ev, comp_ev = [], []
 
-    def issue_copy(slot):
+    def issue_upload(slot):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[slot])          # the compute that last read this slot has finished
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             c0.record(copy_stream)
-            for side in host:
-                for k, t in host[side].items():
-                    slots[slot][side][k].copy_(t, non_blocking=True)
+            built = {}
+            for side, h in host.items():
+                s = sides[side]
+                csr = MultiLinkCSR(h["ep_l"], h["ptr_l"], h["sup_l"], n_nb=s["csr"].n_nb, device=dev)
+                x = torch.empty(h["x"].shape, dtype=torch.float32, device=dev)
+                x.copy_(h["x"], non_blocking=True)
+                for t in (csr.end_points, csr.support, csr.cat_indptr, x):
+                    for st in consumers:
+                        t.record_stream(st)
+                built[side] = (csr, x)
             c1.record(copy_stream)
             copy_ev.append((c0, c1))
             ready[slot].record(copy_stream)
+            slots[slot] = built
 
     counter = [0]
 
@@ -599,17 +822,17 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
         i = counter[0]
         counter[0] += 1
         slot = i % 2
-        main = torch.cuda.current_stream()
         main.wait_event(ready[slot])
-        issue_copy((i + 1) % 2)                         # prefetch the next step's inputs
+        built = slots[slot]
+        issue_upload((i + 1) % 2)                       # prefetch the next step's inputs
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(main)
         losses = {}
 
         def one_side(side):
-            b, s = slots[slot][side], sides[side]
-            x = b["x"].detach().requires_grad_(True)
-            csr = MultiLinkCSR.from_device(b["ep"], b["sup"], b["ptr"], R, s["n_dst"], s["csr"].n_nb)
+            s = sides[side]
+            csr, x = built[side]
+            x = x.requires_grad_(True)
             for p in s["agg"].parameters():
                 p.grad = None
             xin = x if s["plan"] is None else sgd.halo_exchange(x, s["plan"])
@@ -622,19 +845,18 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
             # the two directions are independent: each on its own stream, as in the device-resident step, so
             # one direction's plan rebuild and small launches fill the gaps of the other's
             with runtime.fork_join(side_streams) as run:
-                for i, side in enumerate(("user", "item")):
-                    run(i, lambda side=side: one_side(side))
+                for k, side in enumerate(("user", "item")):
+                    run(k, lambda side=side: one_side(side))
         else:
             for side in ("user", "item"):
                 one_side(side)
         total = losses["user"] + losses["item"]
-        free[slot].record(main)
         g1.record(main)
         comp_ev.append((g0, g1))
         return float(total.item())   # D2H read of the step's result
 
     steps = max(3, min(args.steps, 50))
-    issue_copy(0)
+    issue_upload(0)
     for _ in range(4):
         step()
     barrier()
@@ -655,12 +877,15 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
         ms = float(t.item())
     return dict(value=total_edges / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=4,
+                call="MultiLinkCSR(end_points_l, indptr_l, support_l) from pinned per-level host lists -> MultiLinkGCNAggregator(x, csr) "
+                     "-> loss.backward() -> loss.item()",
                 breakdown=dict(h2d_ms=round(h2d_ms, 4), h2d_gbs=round(h2d / (h2d_ms * 1e-3) / 1e9, 2) if h2d_ms else None,
                                gpu_compute_ms=round(gpu_ms, 4),
                                note="copy-stream and compute-stream busy time per step (they overlap); the step time "
                                     "also contains host launch latency and the blocking loss read-back"),
-                includes="H2D of CSR+features from pinned memory (double-buffered: the next step's copy overlaps this step's compute), device plan rebuild "
-                "(transpose + schedules), " + ("halo exchange, " if world > 1 else "the two directions on two streams, ") + "fwd+bwd, scalar loss read-back"
+                includes="H2D of the 3*R per-level lists + features of both directions from pinned memory (double-buffered: the next step's "
+                "copy overlaps this step's compute), device-side concatenation, device plan rebuild (transpose + schedules), "
+                + ("halo exchange, " if world > 1 else "the two directions on two streams, ") + "fwd+bwd, scalar loss read-back"
                 + ("; per rank, halo index plan reused" if world > 1 else ""))
 
 
@@ -694,6 +919,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.check:
+        if world < 2:
+            raise SystemExit("bench.py --check compares the partitioned NCCL path with the whole graph: launch it with N >= 2 ranks")
+        rc = run_check(args, rank, world, local_rank)
+        dist.barrier()
+        dist.destroy_process_group()
+        return rc
     result, wl = run_gpu_arm(args, rank, world, local_rank)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -46,6 +46,11 @@ int sg_abi_version(void);
 /* Number of kernels this library has launched (process-wide) since the last reset. */
 long long sg_launch_count(void);
 void sg_launch_count_reset(void);
+/* Development only (tools/, A/B measurements): set a process-wide tuning option; 0 is always the shipped
+ * behaviour and the product path never calls this.  Options: 0 gather variant (1 = bulk-copy staged segments),
+ * 1 gather blocks per SM, 2 GEMM TMEM hand-back arrival (1 = release), 3 GEMM chain length in k-blocks,
+ * 4 in-kernel split of a raw B operand.  Nothing in the library reads the environment. */
+int sg_dev_option(int which, int value);
 
 /* ------------------------------------------------------------------------------------------
  * A7  Segment bookkeeping (bit-exact integer work)
@@ -158,7 +163,8 @@ int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x /*n_nb,D*/,
 /* Same aggregation written as the pre-split A operand of sg_gemm_tf32x3: row i of agg_hi / agg_lo
  * (ld_agg floats, ld_agg >= R*D + R, multiple of 4) holds the R aggregated D-vectors followed by the
  * R support sums wsum[i, r] at column R*D + r, each value x stored as (tf32-exact hi, x - hi).
- * Columns beyond R*D + R are not written.  D must be 16, 32, 64 or 128. */
+ * Columns beyond R*D + R are not written.  D must be 16, 32, 64 or 128.  agg_lo == NULL writes the same
+ * row layout as plain fp32 into agg_hi (the raw A operand of sg_gemm_tf32x3). */
 int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const float *x, const float *support,
                                const int32_t *end_points, const int32_t *cat_indptr, int R, int n_dst, int n_nb,
                                int nnz, int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream);
@@ -176,7 +182,9 @@ int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, 
 /* ------------------------------------------------------------------------------------------
  * A1 (transform part)  fp32-accurate GEMM on tcgen05 tensor cores (3xTF32 split)
  * replaces the R FullyConnected calls + add_n of aggregators.py:141-159 (cuBLAS sgemm inside
- * MXNet) and their backward.  Operands arrive pre-split (x = hi + lo, sg_split_tf32):
+ * MXNet) and their backward.  An operand is either pre-split (x = hi + lo, sg_split_tf32: pass both
+ * pointers) or plain fp32 (pass it as *_hi with *_lo == NULL: the kernel splits every tile in shared
+ * memory — half the operand bytes and no producer pass; B may be raw only when A is):
  *   mn_major == 0:  D[M,N] = A[M,K] . B[N,K]^T      A, B row-major, K contiguous (lda, ldb)
  *   mn_major == 1:  D[M,N] = A[K,M]^T . B[K,N]      A, B row-major, M / N contiguous (reduction over rows)
  * lda / ldb must be multiples of 4 floats and the operands 16-byte aligned (TMA).
@@ -302,6 +310,16 @@ int sg_multi_adam(float *const *params, float *const *grads, float *const *ms, f
                   const long long *numels, const void *work, int n_work, float lr_t, float beta1, float beta2,
                   float eps, float wd, float rescale, const float *clip_out2, int write_back_grad,
                   sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement aid (bench.py roofline; no reference counterpart): random-row gather ceiling.
+ * `blocks` x 16 lane groups each read `reads_per_group` (multiple of 8) rows of 64 floats at hashed
+ * positions of table[n_rows, 64] — the access shape of the aggregation gather with no index load,
+ * weight or epilogue — and write one row: out[blocks * 16, 64].  Bytes moved =
+ * blocks * 16 * reads_per_group * 256.
+ * ---------------------------------------------------------------------------------------- */
+int sg_row_gather_probe(float *out, const float *table, int n_rows, int reads_per_group, int blocks,
+                        unsigned seed, sg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SIGNATURES = {
     "sg_abi_version": (_c_int, []),
     "sg_launch_count": (ctypes.c_longlong, []),
     "sg_launch_count_reset": (None, []),
+    "sg_dev_option": (_c_int, [_c_int, _c_int]),
     "sg_seg_ids": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_p]),
     "sg_csr_transpose_ws_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "sg_csr_transpose": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_p, _c_sz, _c_p]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "sg_colsum": (_c_int, [_c_p] * 3 + [_c_int] * 3 + [_c_p, _c_p]),
     "sg_split_tf32": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p]),
     "sg_act_bwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_int, _c_int, ctypes.c_float, _c_p]),
+    "sg_row_gather_probe": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, ctypes.c_uint, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),
 }
 
@@ -106,6 +108,14 @@ def check(rc, what):
         if rc == 1:
             raise ValueError(f"{what}: {msg}")
         raise StarGCNError(f"{what} failed (code {rc}): {msg}")
+
+
+DEV_OPTIONS = {"gather_variant": 0, "gather_grid": 1, "gemm_arrive": 2, "gemm_chain": 3, "gemm_split_b": 4}
+
+
+def dev_option(name, value):
+    """Development only: set a tuning option of the library (see sg_dev_option); 0 = shipped behaviour."""
+    check(load().sg_dev_option(DEV_OPTIONS[name], int(value)), "sg_dev_option")
 
 
 def launch_count():

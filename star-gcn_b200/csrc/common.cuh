@@ -37,16 +37,30 @@ int fail(int code, const char *fmt, ...);
 
 inline bool valid_req(int req) { return req == SG_REQ_NULL || req == SG_REQ_WRITE || req == SG_REQ_ADD; }
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }
+
+// Development options (sg_dev_option): process-wide integers a tuning tool sets EXPLICITLY through the C ABI —
+// the product path never sets them and nothing reads the environment.  Every option's 0 is the shipped behaviour.
+enum DevOption {
+  SG_DEV_GATHER_VARIANT = 0,   // 1: bulk-copy (TMA) staged index/weight segments, warp per work item (gather.cu)
+  SG_DEV_GATHER_GRID = 1,      // blocks per SM of the grid-stride gather launches (0 = 32)
+  SG_DEV_GEMM_ARRIVE = 2,      // 1: cluster-scope RELEASE arrival when a TMEM buffer is handed back (0 = relaxed)
+  SG_DEV_GEMM_CHAIN = 3,       // k-blocks per TMEM accumulation chain (0 = kChainKBlocks)
+  SG_DEV_GEMM_SPLIT_B = 4,     // in-kernel-split GEMM, K-major: 1 = also split B in the kernel when it arrives raw
+  SG_DEV_COUNT = 8
+};
+int dev_option(int which);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -16,8 +16,6 @@
 // Reference kernels replaced: SegTakeKCorrBackwardEmbed1Kernel (seg_op.cu:682-722),
 // SegTakeKCorrBackwardEmbed2Kernel (seg_op.cu:747-790), SegPoolKernel sum/mean
 // (seg_op.cu:1057-1135), SegPoolBackwardKernel sum/mean (seg_op.cu:1171-1215).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -330,6 +328,135 @@ __global__ void __launch_bounds__(256, 1) gather_rows_fast_kernel(const GatherAr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Staged variant (development option SG_DEV_GATHER_VARIANT = 1; measured against the default in
+// profiles/r02_summary.md): ONE WARP per work item; lane 0 bulk-copies the item's index and weight
+// segments global -> shared with cp.async.bulk (the TMA unit's 1-D copy, completion on an mbarrier) one
+// item ahead of the row loads, the two half-warps then walk alternate 8-edge batches reading indices /
+// weights from shared memory (broadcast reads) and their two partial rows are combined with one
+// shuffle-xor before the store.  Rows of 64 floats, weights w[p], write semantics (the fused
+// aggregation's launches); only used for long work items (>= 16 edges on average).
+// ------------------------------------------------------------------------------------------
+constexpr int kStageElems = 264;   // 256-edge chunk + alignment slack on both ends (16-byte bulk copies)
+
+__device__ __forceinline__ uint32_t gsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool WSUM>
+__global__ void __launch_bounds__(256) gather_rows_staged_kernel(const GatherArgs a) {
+  __shared__ __align__(16) int32_t s_idx[8][2][kStageElems];
+  __shared__ __align__(16) float s_w[8][2][kStageElems];
+  __shared__ uint64_t s_bar[8][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int gwarp = blockIdx.x * 8 + warp, n_warps = gridDim.x * 8;
+  const int n_items = a.hdr->n_items;
+  const int nnz4 = (a.hdr->nnz + 3) & ~3;
+  const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src) + l16;
+
+  if (lane == 0) {
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gsmem_u32(&s_bar[warp][b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  auto prefetch = [&](int it, int buf) {   // lane 0 only
+    const int4 d = __ldg(a.items + it);
+    const int p0 = d.x & ~3;
+    int p1 = (d.y + 3) & ~3;
+    if (p1 > nnz4) p1 = nnz4;
+    const uint32_t bytes = (uint32_t)(p1 - p0) * 4u;
+    const uint32_t bar = gsmem_u32(&s_bar[warp][buf]);
+    if (bytes == 0) {   // empty item: complete the phase without a copy
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+      return;
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gsmem_u32(&s_idx[warp][buf][0])), "l"(a.idx + p0), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gsmem_u32(&s_w[warp][buf][0])), "l"(a.w + p0), "r"(bytes), "r"(bar) : "memory");
+  };
+
+  int k = 0;
+  if (gwarp < n_items && lane == 0) prefetch(gwarp, 0);
+  for (int it = gwarp; it < n_items; it += n_warps, ++k) {
+    const int buf = k & 1;
+    const uint32_t phase = (uint32_t)(k >> 1) & 1u;
+    const int4 d = __ldg(a.items + it);
+    if (lane == 0 && it + n_warps < n_items) prefetch(it + n_warps, buf ^ 1);
+    {
+      const uint32_t bar = gsmem_u32(&s_bar[warp][buf]);
+      asm volatile(
+          "{\n\t"
+          ".reg .pred P1;\n\t"
+          "LAB_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+          "@P1 bra DONE;\n\t"
+          "bra LAB_WAIT;\n\t"
+          "DONE:\n\t"
+          "}" ::"r"(bar), "r"(phase) : "memory");
+    }
+    const int32_t *sidx = &s_idx[warp][buf][0] + (d.x & 3);
+    const float *sw = &s_w[warp][buf][0] + (d.x & 3);
+    const int n = d.y - d.x;
+    float4 acc[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wacc = 0.f;
+    // batches of 16 edges: half-warp h takes edges [e0 + 8h, e0 + 8h + 8)
+    for (int e0 = 0; e0 < n; e0 += 16) {
+      const int eb = e0 + half * 8;
+      int id[8];
+      float wv[8];
+      float4 val[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) id[u] = eb + u < n ? sidx[eb + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) val[u] = id[u] >= 0 ? __ldg(src + (long long)id[u] * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = id[u] >= 0 ? sw[eb + u] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if constexpr (WSUM) wacc += wv[u];
+        acc[u & 3].x = fmaf(wv[u], val[u].x, acc[u & 3].x);
+        acc[u & 3].y = fmaf(wv[u], val[u].y, acc[u & 3].y);
+        acc[u & 3].z = fmaf(wv[u], val[u].z, acc[u & 3].z);
+        acc[u & 3].w = fmaf(wv[u], val[u].w, acc[u & 3].w);
+      }
+    }
+    float4 r;
+    r.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+    r.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+    r.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
+    r.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+    r.x += __shfl_xor_sync(0xffffffffu, r.x, 16);
+    r.y += __shfl_xor_sync(0xffffffffu, r.y, 16);
+    r.z += __shfl_xor_sync(0xffffffffu, r.z, 16);
+    r.w += __shfl_xor_sync(0xffffffffu, r.w, 16);
+    if constexpr (WSUM) wacc += __shfl_xor_sync(0xffffffffu, wacc, 16);
+    if (half == 0) {
+      if (d.w >= 0) {
+        reinterpret_cast<float4 *>(a.partial + (long long)d.w * 64)[l16] = r;
+        if (WSUM && l16 == 0) a.partial_wsum[d.w] = wacc;
+      } else {
+        int rel = 0, row = d.z;
+        if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
+        float *orow = a.out + ((long long)row * a.ld_out + rel * 64);
+        if (a.out_lo) {
+          const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
+          reinterpret_cast<float4 *>(orow)[l16] = hi;
+          reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[l16] = make_float4(r.x - hi.x, r.y - hi.y, r.z - hi.z, r.w - hi.w);
+        } else {
+          reinterpret_cast<float4 *>(orow)[l16] = r;
+        }
+        if (WSUM && l16 == 0) store_wsum_at(a, row, rel, wacc);
+      }
+    }
+    __syncwarp();   // every lane is done with this buffer before lane 0 refills it (two items ahead)
+  }
+}
+
 // Second pass: fixed-order sum of the partial rows of every split segment.
 template <int VEC, int LPR, int NV>
 __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
@@ -416,16 +543,13 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
   }
 }
 
-// Tuning knob (development only): SG_GATHER_GRID = blocks per SM the grid-stride kernels are launched with.
 // Grid-stride launches use at most 32 blocks per SM (5-6 resident at a time): work items differ in length
 // (chunks of up to 256 edges), so several waves of smaller blocks balance better than one resident wave —
 // measured on the ML-10M shape, sum of the four launches: 0.99 ms at 6 blocks/SM, 0.86 at 16, 0.82 at
-// 24..64, 0.86 with one item per group (tools/sweep_gather.py).
-static long long grid_cap() {  // read on every call: tools/sweep_gather.py changes it inside one process
-  const char *e = getenv("SG_GATHER_GRID");
-  int v = e ? atoi(e) : 32;
-  if (v < 1) v = 32;
-  return (long long)num_sms() * v;
+// 24..64, 0.86 with one item per group.  (Development option SG_DEV_GATHER_GRID overrides it for sweeps.)
+static long long grid_cap() {
+  const int v = dev_option(SG_DEV_GATHER_GRID);
+  return (long long)num_sms() * (v > 0 ? v : 32);
 }
 
 template <int VEC, int LPR, int NV>
@@ -497,10 +621,20 @@ static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n
                : launch_fast<LPR, NV, UNROLL, 1, false>(a, K, n_items_cap, n_long_cap, st);
 }
 
-// Tuning knob (development only): SG_GATHER_SHAPE=1|2|3 forces a lane layout / batch size of the D=64 fast path.
-static int gather_shape() {
-  const char *e = getenv("SG_GATHER_SHAPE");
-  return e ? atoi(e) : 0;
+template <bool WSUM>
+static int launch_staged(const GatherArgs &a, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, 8);
+  const long long cap = grid_cap();
+  if (blocks > cap) blocks = cap;
+  gather_rows_staged_kernel<WSUM><<<(unsigned)blocks, 256, 0, st>>>(a);
+  SG_LAUNCHED("gather_rows_staged_kernel");
+  if (n_long_cap > 0) {
+    long long cb = ceil_div<long long>(n_long_cap, 16);
+    if (cb > cap) cb = cap;
+    combine_partials_kernel<4, 16, 1><<<dim3((unsigned)cb, 1, 1), 256, 0, st>>>(a);
+    SG_LAUNCHED("combine_partials_kernel");
+  }
+  return SG_OK;
 }
 
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st) {
@@ -539,9 +673,9 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
       case 16: return dispatch_fast_mode<4, 1, 8>(a, K, n_items_cap, n_long_cap, st);
       case 32: return dispatch_fast_mode<8, 1, 8>(a, K, n_items_cap, n_long_cap, st);
       case 64:
-        if (gather_shape() == 1) return dispatch_fast_mode<8, 2, 4>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 2) return dispatch_fast_mode<8, 2, 8>(a, K, n_items_cap, n_long_cap, st);
-        if (gather_shape() == 3) return dispatch_fast_mode<16, 1, 8>(a, K, n_items_cap, n_long_cap, st);
+        if (dev_option(SG_DEV_GATHER_VARIANT) == 1 && a.hdr && K == 1 && a.w && !a.perm && !a.inv_len_indptr && !a.mean &&
+            a.req == SG_REQ_WRITE && nnz >= 16LL * n_items_cap && aligned(a.idx, 16) && aligned(a.w, 16))
+          return a.wsum ? launch_staged<true>(a, n_items_cap, n_long_cap, st) : launch_staged<false>(a, n_items_cap, n_long_cap, st);
         // short segments (fewer than 16 edges per work item on average, the user side of a rating graph):
         // batches of 4 — as fast as batches of 8 there (0.263 ms both) with 46 instead of 64 registers
         if (nnz < 16LL * n_items_cap) return dispatch_fast_mode<16, 1, 4>(a, K, n_items_cap, n_long_cap, st);

@@ -9,20 +9,21 @@
 // and the kernel accumulates  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  into one fp32 TMEM accumulator
 // (the dropped A_lo.B_lo term is ~2^-22 relative).
 //
-// Kernel shape (persistent: one CTA per SM loops over 128 x 256 output tiles, 320 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) -> STAGES-deep smem ring
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
-//               (M=128, N=BN, K=8) from smem descriptors; tcgen05.commit frees the stage
-//   warps 2-9   epilogue: drain each TMEM chain (tcgen05.ld 32x32b.x32) into fp32 register
-//               accumulators; at the end of a tile bias + activation and coalesced stores through a
-//               padded smem transpose, while the MMA warp already runs the next tile's chains
+// Kernel shape (persistent; a CTA PAIR — cluster of 2, tcgen05 cta_group::2 — owns one 256 x 256 output tile):
+//   TMA warp    cp.async.bulk.tensor (SWIZZLE_128B) -> 3-deep smem ring, each CTA ITS 128 rows of A and ITS half of B
+//   MMA warp    (leader CTA) one elected lane issues tcgen05.mma.cta_group::2.kind::tf32 (M=256, N<=256, K=8) from
+//               smem descriptors; tcgen05.commit (multicast) frees the stage in both CTAs
+//   8 epilogue warps  drain each TMEM chain (tcgen05.ld 32x32b.x32) into fp32 register accumulators; at the end
+//               of a tile bias + activation and coalesced stores through a padded smem transpose, while the MMA
+//               warp already runs the next tile's chains
+//   4 splitter warps (tf32x3_gemm_split_kernel) do the hi/lo split of operands that arrive as plain fp32
+// Two kernels: tf32x3_gemm_pair_kernel takes operands pre-split by a producer pass (small Dense layers, weights);
+// tf32x3_gemm_split_kernel splits inside the kernel (the large activations: agg, gZ).
 // Operand layouts: K-major (A[M,K], B[N,K] row-major; forward and dAgg) or MN-major (A[K,M],
 // B[K,N] row-major; the weight gradient, whose reduction axis is the node axis) — the latter
 // loads [32 floats x 32 k-rows] swizzle atoms (one TMA box each) and sets the a_major/b_major
 // bits of the instruction descriptor.  Split-K partials are summed in a fixed order.
 #include <cuda.h>
-
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -41,12 +42,11 @@ struct GemmArgs {
   int kb_total;      // number of BK-wide k-blocks
   int kb_per_split;
   int tiles_m, tiles_n, splits;
-  int chain_kb;      // k-blocks per TMEM accumulation chain (kChainKBlocks; tuning knob SG_GEMM_CHAIN)
-  int first_pass;    // 0 normally; 2 = issue only the hi.hi product (timing experiment SG_GEMM_PASSES=1, wrong numerics)
+  int chain_kb;      // k-blocks per TMEM accumulation chain (kChainKBlocks)
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
   const float *bias; // optional [N], added before the activation
-  int relaxed_arrive; // pair kernel: hand the TMEM buffer back with a relaxed arrival (SG_GEMM_ARRIVE=relaxed)
+  int relaxed_arrive; // hand the TMEM buffer back with a relaxed arrival (default; see mbar_arrive_leader_relaxed)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -144,212 +144,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // while the MMA warp fills the other TMEM buffer (2 x BN columns = all 512 TMEM columns).  The chain
 // length trades time for accuracy — forward transform / error of one fused layer vs the fp64 answer:
 //   chain 2: 0.160 ms / 7.7e-7    chain 4: 0.136 ms / 8.8e-7    chain 8: 0.122 ms / 1.3e-6
-// (a plain fp32 FMA GEMM is at 1e-7 .. 3e-7).  Tuning knob: SG_GEMM_CHAIN.
+// (a plain fp32 FMA GEMM is at 1e-7 .. 3e-7).
 // ---------------------------------------------------------------------------------------------
 constexpr int kChainKBlocks = 4;  // 4 k-blocks x 3 hi/lo products x 4 = 48 MMAs per TMEM chain
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int BN, int STAGES, bool MN_MAJOR>
-__global__ void __launch_bounds__(kGemmThreads, 1) tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi,
-                                                                      const __grid_constant__ CUtensorMap map_a_lo,
-                                                                      const __grid_constant__ CUtensorMap map_b_hi,
-                                                                      const __grid_constant__ CUtensorMap map_b_lo,
-                                                                      const GemmArgs g) {
-  static_assert(BN == 256, "two BN-column accumulators must fill the 512 TMEM columns");
-  // one stage = the four operand tiles of ONE k-block (A_hi, A_lo, B_hi, B_lo), each fetched once and
-  // used by the three hi/lo products
-  constexpr int A_BYTES = kBM * kBK * 4;
-  constexpr int B_BYTES = BN * kBK * 4;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr int STG_FLOATS = 32 * 33;  // per-epilogue-warp transpose tile (padded: conflict-free both ways)
-  constexpr uint32_t IDESC_BASE = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
-                                  ((MN_MAJOR ? 1u : 0u) << 15) | ((MN_MAJOR ? 1u : 0u) << 16) |
-                                  ((uint32_t)(kBM >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
-  __shared__ uint64_t full_bar[STAGES];
-  __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t tmem_full_bar[2];
-  __shared__ uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_smem;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  // persistent tile loop: tile -> (n tile fastest, then m tile, then split) so the CTAs that share an
-  // A tile run at the same time and find it in L2
-  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;
-  const int n_tiles = tiles_mn * g.splits;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
-    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kEpiWarps); }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<2 * BN>(&tmem_base_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int v = 0;  // running stage counter across tiles
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-        const int m0 = (rem / tiles_n) * kBM, n0 = (rem % tiles_n) * BN;
-        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
-          const int s = v % STAGES;
-          const uint32_t ph = (v / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
-          if constexpr (MN_MAJOR) {  // one [32 floats x 32 k-rows] swizzle atom per load
-#pragma unroll
-            for (int a = 0; a < kBM / 32; ++a) {
-              tma_load_2d(sa_hi + a * (kBK * 128), &map_a_hi, &full_bar[s], m0 + a * 32, kb * kBK);
-              tma_load_2d(sa_lo + a * (kBK * 128), &map_a_lo, &full_bar[s], m0 + a * 32, kb * kBK);
-            }
-#pragma unroll
-            for (int a = 0; a < BN / 32; ++a) {
-              tma_load_2d(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], n0 + a * 32, kb * kBK);
-              tma_load_2d(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], n0 + a * 32, kb * kBK);
-            }
-          } else {
-            tma_load_2d(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
-            tma_load_2d(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
-            tma_load_2d(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, n0);
-            tma_load_2d(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int v = 0, chain = 0;  // running counters across tiles
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-        const int n0 = (rem % tiles_n) * BN;
-        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-        const int n_kb = kb_end - kb_begin;
-        // UMMA N for this tile: the valid columns rounded up to 16 (a partly empty last n-tile costs less)
-        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
-        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
-        for (int i = 0; i < n_kb; ++i, ++v) {
-          const int s = v % STAGES;
-          const uint32_t ph = (v / STAGES) & 1;
-          const int vin = i % g.chain_kb;
-          const int buf = chain & 1;
-          if (vin == 0) {  // start of a chain: the epilogue warps must have drained this buffer
-            mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
-                         sb_lo = sb_hi + B_BYTES;
-#pragma unroll
-          for (int pass = g.first_pass; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
-            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              uint64_t da, db;
-              if constexpr (MN_MAJOR) {  // boxes [32 floats x 32 k-rows] 4096 B apart (LBO); 4-row swizzle groups
-                                         // 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
-                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
-                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
-              } else {                   // rows of 128 B, 8-row groups 1024 B apart; 8 floats = 32 B per MMA
-                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
-                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
-              }
-              umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != g.first_pass) || (k != 0));
-            }
-          }
-          umma_commit(&empty_bar[s]);
-          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
-            umma_commit(&tmem_full_bar[buf]);
-            ++chain;
-          }
-        }
-      }
-    }
-  } else {
-    // epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half h
-    const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
-    const int cbase = h * (BN / 2);
-    float *stg = stg_all + (warp - 2) * STG_FLOATS;
-    const bool v_ok = true;
-    (void)v_ok;
-    int chain = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-      const int m0 = (rem / tiles_n) * kBM, n0 = (rem % tiles_n) * BN;
-      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
-      const bool active = n0 + cbase < g.N;  // warp-uniform
-      float racc[BN / 2];
-#pragma unroll
-      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
-      for (int c = 0; c < n_chains; ++c, ++chain) {
-        const int buf = chain & 1;
-        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
-        tc_fence_after();
-        if (active) {
-#pragma unroll
-          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-      }
-      if (active) {
-        // thread = row in registers -> 32x32 transpose through padded smem -> lane = column: every store
-        // instruction writes 128 contiguous bytes of one output row
-        float *dbase = g.D + (long long)z * g.split_stride;
-        const int row0 = m0 + q * 32;
-#pragma unroll
-        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
-          const int col = n0 + cbase + ch * 32 + lane;
-          if (n0 + cbase + ch * 32 >= g.N) break;  // warp-uniform
-          float bias = 0.f;
-          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
-          __syncwarp();
-          const int rows = min(32, g.M - row0);
-          for (int rr = 0; rr < rows; ++rr) {
-            float x = stg[rr * 33 + lane] + bias;
-            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
-            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,8 +203,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // arrive o
 // flight — the 128 output-row stores of the tile it has just written — before the TMEM buffer is handed back
 // (ncu source page, final capture of round 1: 15-26 % of all warp samples of the pair kernel sit on the
 // ERRBAR / SYNCS.ARRIVE pair of this arrival with stall_membar).  The hand-over only has to order the
-// tcgen05.ld reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already do.  Opt-in
-// (SG_GEMM_ARRIVE=relaxed) until it has been through the GPU suite.
+// tcgen05.ld reads, which tcgen05.wait::ld (the values are in registers before the arrival is issued) +
+// tcgen05.fence::before_thread_sync already do.  Default since round 2 (full GPU suite green).
 __device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t *bar) {
   asm volatile(
       "{\n\t"
@@ -517,7 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
                          sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-          for (int pass = g.first_pass; pass < 3; ++pass) {
+          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
             const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -529,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 da = make_smem_desc(sa + k * 32, 16, 1024, 2);
                 db = make_smem_desc(sb + k * 32, 16, 1024, 2);
               }
-              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != g.first_pass) || (k != 0));
+              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != 0) || (k != 0));
             }
           }
           umma_commit_pair(&empty_bar[s]);
@@ -545,6 +346,279 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     const int h = (warp - 2) >> 2;
     const int cbase = h * (BN / 2);
     float *stg = stg_all + (warp - 2) * STG_FLOATS;
+    int chain = 0;
+    for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+      const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
+      const bool active = n0 + cbase < g.N && m0 < g.M;  // warp-uniform
+      float racc[BN / 2];
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
+      for (int c = 0; c < n_chains; ++c, ++chain) {
+        const int buf = chain & 1;
+        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+        tc_fence_after();
+        if (active) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (g.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty_bar[buf]);
+          else mbar_arrive_leader(&tmem_empty_bar[buf]);
+        }
+      }
+      if (active) {
+        float *dbase = g.D + (long long)z * g.split_stride;
+        const int row0 = m0 + q * 32;
+#pragma unroll
+        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+          const int col = n0 + cbase + ch * 32 + lane;
+          if (n0 + cbase + ch * 32 >= g.N) break;
+          float bias = 0.f;
+          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
+          __syncwarp();
+          const int rows = min(32, g.M - row0);
+          for (int rr = 0; rr < rows; ++rr) {
+            float x = stg[rr * 33 + lane] + bias;
+            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
+            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel with the hi/lo operand split done INSIDE the kernel.
+//
+// The pre-split kernels above stream 8 bytes per operand element (hi + lo) through the L2->SM fabric and
+// need a producer pass that writes both halves to HBM.  Here an operand arrives as plain fp32: TMA lands
+// the raw tile in the "hi" slot of the stage, four splitter warps rewrite it in place as the TF32-exact
+// high part and store the remainder to the "lo" slot (the split is element-wise, so the swizzled layout
+// TMA produced is preserved), `fence.proxy.async` makes the generic-proxy stores visible to the tensor
+// core's async-proxy reads, and a second barrier (on the leader CTA, 4 warps x 2 CTAs arrivals) tells the
+// MMA warp that the stage is ready in BOTH CTAs.  A is always split in the kernel; B either arrives
+// pre-split (small weight matrices, split once per call) or raw (SPLIT_B: the weight gradient, whose B
+// operand is the aggregated feature matrix).
+//
+// 512 threads = 4 warpgroups with their own register budgets (setmaxnreg): WG0 = TMA warp, MMA warp, TMEM
+// allocator (40 registers), WG1-2 = 8 epilogue warps holding the 128 fp32 accumulators of the chained TMEM
+// drain (208), WG3 = 4 splitter warps (56); 128 x (40 + 208 + 208 + 56) = the whole register file.
+// Each CTA's TMA loads complete on its OWN full barrier (the splitter warps of that CTA wait there).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSplitThreads = 512;
+constexpr int kSplitterWarps = 4;
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// hi/lo split of one 16 KB operand tile by the 128 splitter threads (conflict-free 16-byte accesses)
+__device__ __forceinline__ void split_tile_16k(uint8_t *hi_slot, uint8_t *lo_slot, int st) {
+  constexpr int kVecs = 16384 / 16 / (kSplitterWarps * 32);  // 8 float4 per thread
+  float4 v[kVecs];
+#pragma unroll
+  for (int i = 0; i < kVecs; ++i) v[i] = reinterpret_cast<const float4 *>(hi_slot)[i * (kSplitterWarps * 32) + st];
+#pragma unroll
+  for (int i = 0; i < kVecs; ++i) {
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+    reinterpret_cast<float4 *>(hi_slot)[i * (kSplitterWarps * 32) + st] = h;
+    reinterpret_cast<float4 *>(lo_slot)[i * (kSplitterWarps * 32) + st] =
+        make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+  }
+}
+
+template <int STAGES, bool MN_MAJOR, bool SPLIT_B>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
+    tf32x3_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+                             const __grid_constant__ CUtensorMap map_b_lo, const GemmArgs g) {
+  constexpr int BN = 256;
+  constexpr int A_BYTES = kBM * kBK * 4;   // this CTA's 128 rows of A (one slot; hi and lo slots per stage)
+  constexpr int B_BYTES = 128 * kBK * 4;   // this CTA's half of the B tile
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int TX_BYTES = A_BYTES + (SPLIT_B ? B_BYTES : 2 * B_BYTES);   // what TMA delivers per stage and CTA
+  constexpr int STG_FLOATS = 32 * 33;
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
+                                  ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+  __shared__ uint64_t full_bar[STAGES];    // this CTA's TMA bytes
+  __shared__ uint64_t empty_bar[STAGES];   // MMAs that read the stage have completed (multicast commit)
+  __shared__ uint64_t split_bar[STAGES];   // leader only: stage split in both CTAs (2 x kSplitterWarps arrivals)
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];   // leader only
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;
+  const int n_tiles = tiles_mn * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b_hi);
+    if constexpr (!SPLIT_B) tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 2 * kSplitterWarps);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    reg_dec<40>();
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer (both CTAs): raw A tile -> hi slot; B pre-split (hi, lo) or raw -> hi slot ----
+      int v = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const int nb0 = n0 + (int)rank * (n_eff >> 1);
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], TX_BYTES);
+          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sb_hi = sa_hi + 2 * A_BYTES, *sb_lo = sb_hi + B_BYTES;
+          if constexpr (MN_MAJOR) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              tma_load_2d(sa_hi + a * (kBK * 128), &map_a, &full_bar[s], m0 + a * 32, kb * kBK);
+              tma_load_2d(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + a * 32, kb * kBK);
+              if constexpr (!SPLIT_B) tma_load_2d(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
+            }
+          } else {
+            tma_load_2d(sa_hi, &map_a, &full_bar[s], kb * kBK, m0);
+            tma_load_2d(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
+            if constexpr (!SPLIT_B) tma_load_2d(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
+          }
+        }
+      }
+    } else if (warp == 1 && leader && lane == 0) {
+      // ---- MMA issuer (leader CTA): waits for the split stage of BOTH CTAs ----
+      int v = 0, chain = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int n0 = (rem % tiles_n) * BN;
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        const int n_kb = kb_end - kb_begin;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        for (int i = 0; i < n_kb; ++i, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          const int vin = i % g.chain_kb;
+          const int buf = chain & 1;
+          if (vin == 0) {
+            mbar_wait_cluster(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait_cluster(&split_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
+                         sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
+            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              uint64_t da, db;
+              if constexpr (MN_MAJOR) {
+                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
+                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
+              } else {
+                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+              }
+              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != 0) || (k != 0));
+            }
+          }
+          umma_commit_pair(&empty_bar[s]);
+          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
+            umma_commit_pair(&tmem_full_bar[buf]);
+            ++chain;
+          }
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ---- splitter warps (both CTAs) ----
+    reg_dec<56>();
+    const int st = threadIdx.x - 12 * 32;
+    int v = 0;
+    for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+      const int z = tile / tiles_mn;
+      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
+        const int s = v % STAGES;
+        const uint32_t ph = (v / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t *sa_hi = smem + s * STAGE_BYTES;
+        split_tile_16k(sa_hi, sa_hi + A_BYTES, st);
+        if constexpr (SPLIT_B) split_tile_16k(sa_hi + 2 * A_BYTES, sa_hi + 2 * A_BYTES + B_BYTES, st);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&split_bar[s]);
+      }
+    }
+  } else {
+    // ---- epilogue warps 4..11: TMEM lane quarter q = warp % 4, column half h ----
+    reg_inc<208>();
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const int cbase = h * (BN / 2);
+    float *stg = stg_all + (warp - 4) * STG_FLOATS;
     int chain = 0;
     for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
       const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
@@ -650,9 +724,13 @@ __global__ void __launch_bounds__(256) act_bwd_split_kernel(float *__restrict__ 
       const float gval = __ldg(gout + o);
       x = __ldg(out + o) > 0.f ? gval : slope * gval;
     }
-    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    gz_hi[t] = h;
-    gz_lo[t] = x - h;
+    if (gz_lo) {
+      const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      gz_hi[t] = h;
+      gz_lo[t] = x - h;
+    } else {
+      gz_hi[t] = x;   // plain fp32 for the in-kernel-split GEMM
+    }
   }
 }
 
@@ -675,8 +753,28 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached per thread, keyed by (pointer, shape, box): a training loop calls the same
+// GEMMs on the same caching-allocator blocks every step, and cuTensorMapEncodeTiled costs ~1 us each.
+struct MapKey {
+  const void *ptr; int d0, d1, ld, box, kind;
+  bool operator==(const MapKey &o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && box == o.box && kind == o.kind; }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+constexpr int kMapCacheSlots = 256;
+static thread_local MapSlot g_map_cache[kMapCacheSlots];
+static MapSlot *map_slot(const MapKey &k) {
+  uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= ((uint64_t)(uint32_t)k.d0 << 32 | (uint32_t)k.d1) * 0xC2B2AE3D27D4EB4Full;
+  h ^= ((uint64_t)(uint32_t)k.ld << 32 | (uint32_t)(k.box * 4 + k.kind)) * 0x165667B19E3779F9ull;
+  return &g_map_cache[(h >> 40) % kMapCacheSlots];
+}
+
 // K-major operand X[rows, K] (row-major, ld floats): 2-D map, box = 32 floats x box_rows
 static int make_map_kmajor(CUtensorMap *m, const float *x, int rows, int K, int ld, int box_rows) {
+  const MapKey key{x, rows, K, ld, box_rows, 0};
+  MapSlot *slot = map_slot(key);
+  if (slot->used && slot->key == key) { *m = slot->map; return SG_OK; }
+  const int rc_ = [&]() -> int {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -688,11 +786,18 @@ static int make_map_kmajor(CUtensorMap *m, const float *x, int rows, int K, int 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled (K-major) failed with CUresult %d", (int)r);
   return SG_OK;
+  }();
+  if (rc_ == SG_OK) { slot->key = key; slot->map = *m; slot->used = true; }
+  return rc_;
 }
 
 // MN-major operand X[K, mn] (row-major, ld floats): 2-D map (mn, K), box = 32 floats x 32 k-rows = one
 // SWIZZLE_128B_ATOM_32B box; the kernel places the atoms of a tile 4096 B apart -> smem [atom][k-row][32 floats]
 static int make_map_mnmajor(CUtensorMap *m, const float *x, int K, int mn, int ld) {
+  const MapKey key{x, K, mn, ld, 32, 1};
+  MapSlot *slot = map_slot(key);
+  if (slot->used && slot->key == key) { *m = slot->map; return SG_OK; }
+  const int rc_ = [&]() -> int {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)K};
@@ -704,34 +809,15 @@ static int make_map_mnmajor(CUtensorMap *m, const float *x, int K, int mn, int l
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SG_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", (int)r);
   return SG_OK;
-}
-
-template <int BN, int STAGES, bool MN>
-static int launch_gemm(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
-  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + BN * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<BN, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  g.tiles_m = ceil_div(g.M, kBM);
-  g.tiles_n = ceil_div(g.N, BN);
-  g.splits = splits;
-  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());  // persistent: one CTA per SM
-  tf32x3_gemm_kernel<BN, STAGES, MN><<<grid, kGemmThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-  SG_LAUNCHED("tf32x3_gemm_kernel");
-  return SG_OK;
+  }();
+  if (rc_ == SG_OK) { slot->key = key; slot->map = *m; slot->used = true; }
+  return rc_;
 }
 
 template <int STAGES, bool MN>
 static int launch_gemm_pair(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
   constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel<STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel<STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g.tiles_m = ceil_div(g.M, 256);
   g.tiles_n = ceil_div(g.N, 256);
   g.splits = splits;
@@ -743,14 +829,19 @@ static int launch_gemm_pair(const CUtensorMap (&maps)[4], GemmArgs g, int splits
   return SG_OK;
 }
 
-// SG_GEMM_PAIR=0 selects the single-CTA kernel (A/B comparison); default: CTA pairs
-static bool use_pair() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SG_GEMM_PAIR");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
+template <int STAGES, bool MN, bool SPLIT_B>
+static int launch_gemm_split(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
+  SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_split_kernel<STAGES, MN, SPLIT_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g.tiles_m = ceil_div(g.M, 256);
+  g.tiles_n = ceil_div(g.N, 256);
+  g.splits = splits;
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = (int)(n_tiles < max_pairs ? n_tiles : max_pairs);
+  tf32x3_gemm_split_kernel<STAGES, MN, SPLIT_B><<<2 * pairs, kSplitThreads, smem, st>>>(maps[0], maps[2], maps[3], g);
+  SG_LAUNCHED("tf32x3_gemm_split_kernel");
+  return SG_OK;
 }
 
 static inline int grid_ew(long long n) {
@@ -775,7 +866,8 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
                    const float *bias, int splits, float *split_ws, sg_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SG_REQUIRE(M > 0 && N > 0 && K > 0, "sg_gemm_tf32x3: bad sizes M=%d N=%d K=%d", M, N, K);
-  SG_REQUIRE(D && A_hi && A_lo && B_hi && B_lo, "sg_gemm_tf32x3: null pointer");
+  SG_REQUIRE(D && A_hi && B_hi, "sg_gemm_tf32x3: null pointer");
+  SG_REQUIRE(B_lo || !A_lo, "sg_gemm_tf32x3: a raw B operand (B_lo == NULL) needs a raw A operand (A_lo == NULL) as well");
   SG_REQUIRE(epilogue == 0 || epilogue == 1, "sg_gemm_tf32x3: bad epilogue %d", epilogue);
   SG_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "sg_gemm_tf32x3: operand leading dimensions must be multiples of 4 floats (TMA strides)");
   const uintptr_t al = reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) |
@@ -785,40 +877,31 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
   SG_REQUIRE(splits == 1 || (split_ws && epilogue == 0 && !bias), "sg_gemm_tf32x3: split-K needs a workspace and the plain epilogue");
   GemmArgs g;
   g.M = M; g.N = N; g.epi = epilogue; g.slope = slope; g.bias = bias;
-  {
-    static int chain = -1, passes = -1;
-    if (chain < 0) { const char *e = getenv("SG_GEMM_CHAIN"); chain = e ? atoi(e) : kChainKBlocks; if (chain < 1) chain = 1; }
-    if (passes < 0) { const char *e = getenv("SG_GEMM_PASSES"); passes = e ? atoi(e) : 3; }
-    g.chain_kb = chain;
-    g.first_pass = passes == 1 ? 2 : 0;
-    const char *arr = getenv("SG_GEMM_ARRIVE");
-    g.relaxed_arrive = arr && arr[0] == 'r';
-  }
+  g.chain_kb = dev_option(SG_DEV_GEMM_CHAIN) > 0 ? dev_option(SG_DEV_GEMM_CHAIN) : kChainKBlocks;
+  g.relaxed_arrive = dev_option(SG_DEV_GEMM_ARRIVE) == 0;
   g.kb_total = ceil_div(K, kBK);
   g.kb_per_split = ceil_div(g.kb_total, splits);
   splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split
   if (splits > 1) { g.D = split_ws; g.ldd = N; g.split_stride = (long long)M * N; }
   else { g.D = D; g.ldd = ldd; g.split_stride = 0; }
-  const int BN = 256;
   CUtensorMap maps[4];
   int rc;
   if (mn_major) {
     SG_REQUIRE(M <= lda && N <= ldb, "sg_gemm_tf32x3: MN-major leading dimensions too small");
     if ((rc = make_map_mnmajor(&maps[0], A_hi, K, M, lda)) != SG_OK) return rc;
-    if ((rc = make_map_mnmajor(&maps[1], A_lo, K, M, lda)) != SG_OK) return rc;
+    if ((rc = make_map_mnmajor(&maps[1], A_lo ? A_lo : A_hi, K, M, lda)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
-    if ((rc = make_map_mnmajor(&maps[3], B_lo, K, N, ldb)) != SG_OK) return rc;
-    if (use_pair()) rc = launch_gemm_pair<3, true>(maps, g, splits, st);
-    else rc = launch_gemm<256, 2, true>(maps, g, splits, st);
+    if ((rc = make_map_mnmajor(&maps[3], B_lo ? B_lo : B_hi, K, N, ldb)) != SG_OK) return rc;
+    if (!A_lo) rc = B_lo ? launch_gemm_split<3, true, false>(maps, g, splits, st) : launch_gemm_split<3, true, true>(maps, g, splits, st);
+    else rc = launch_gemm_pair<3, true>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   } else {
-    const int b_rows = use_pair() ? 128 : BN;  // a CTA of a pair loads half of the B tile
     if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[1], A_lo, M, K, lda, kBM)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, b_rows)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[3], B_lo, N, K, ldb, b_rows)) != SG_OK) return rc;
-    if (use_pair()) rc = launch_gemm_pair<3, false>(maps, g, splits, st);
-    else rc = launch_gemm<256, 2, false>(maps, g, splits, st);
+    if ((rc = make_map_kmajor(&maps[1], A_lo ? A_lo : A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, 128)) != SG_OK) return rc;   // a CTA of a pair loads half of the B tile
+    if ((rc = make_map_kmajor(&maps[3], B_lo ? B_lo : B_hi, N, K, ldb, 128)) != SG_OK) return rc;
+    if (!A_lo) rc = B_lo ? launch_gemm_split<3, false, false>(maps, g, splits, st) : launch_gemm_split<3, false, true>(maps, g, splits, st);
+    else rc = launch_gemm_pair<3, false>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   }
   if (splits > 1) {
@@ -844,7 +927,7 @@ int sg_act_bwd_split(float *gz_hi, float *gz_lo, int ldz, const float *gout, con
                      float slope, sg_stream_t stream) {
   SG_REQUIRE(M >= 0 && U >= 0 && ldz >= U, "sg_act_bwd_split: bad sizes");
   if (M == 0 || U == 0) return SG_OK;
-  SG_REQUIRE(gz_hi && gz_lo && gout && out, "sg_act_bwd_split: null pointer");
+  SG_REQUIRE(gz_hi && gout && out, "sg_act_bwd_split: null pointer");
   act_bwd_split_kernel<<<grid_ew((long long)M * ldz), 256, 0, (cudaStream_t)stream>>>(gz_hi, gz_lo, ldz, gout, out, M, U, slope);
   SG_LAUNCHED("act_bwd_split_kernel");
   return SG_OK;

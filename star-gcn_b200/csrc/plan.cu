@@ -13,7 +13,10 @@ namespace sg {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};  // process-wide: autograd runs backward on its own thread
 
+static std::atomic<int> g_dev_options[SG_DEV_COUNT];
+
 char *err_buf() { return g_err; }
+int dev_option(int which) { return which >= 0 && which < SG_DEV_COUNT ? g_dev_options[which].load(std::memory_order_relaxed) : 0; }
 void count_launch(int n) { g_launches += n; }
 
 int fail(int code, const char *fmt, ...) {
@@ -390,6 +393,11 @@ const char *sg_last_error(void) { return sg::err_buf(); }
 int sg_abi_version(void) { return 1; }
 long long sg_launch_count(void) { return sg::g_launches.load(); }
 void sg_launch_count_reset(void) { sg::g_launches.store(0); }
+int sg_dev_option(int which, int value) {
+  SG_REQUIRE(which >= 0 && which < sg::SG_DEV_COUNT, "sg_dev_option: unknown option %d", which);
+  sg::g_dev_options[which].store(value);
+  return SG_OK;
+}
 
 int sg_seg_ids(int32_t *seg_ids, const int32_t *indptr, int n_seg, int nnz, sg_stream_t stream) {
   SG_REQUIRE(n_seg >= 0 && nnz >= 0, "sg_seg_ids: negative size (n_seg=%d nnz=%d)", n_seg, nnz);

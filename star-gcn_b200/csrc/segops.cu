@@ -423,9 +423,9 @@ int sg_multilink_agg_fwd(float *agg, float *wsum, const float *x, const float *s
 int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const float *x, const float *support,
                                const int32_t *end_points, const int32_t *cat_indptr, int R, int n_dst, int n_nb,
                                int nnz, int D, const void *plan, int plan_chunk, float *partial, sg_stream_t stream) {
-  SG_REQUIRE(agg_lo, "sg_multilink_agg_fwd_split: null pointer");
   SG_REQUIRE(ld_agg >= R * D + R && (ld_agg & 3) == 0, "sg_multilink_agg_fwd_split: ld_agg must be a multiple of 4 and >= R*D + R");
-  return multilink_agg_fwd_impl(agg_hi, agg_lo, ld_agg, agg_hi + (size_t)R * D, agg_lo + (size_t)R * D, ld_agg, x, support,
+  // agg_lo == NULL: the same [agg | wsum] row layout, plain fp32 (the in-kernel-split GEMM takes it as it is)
+  return multilink_agg_fwd_impl(agg_hi, agg_lo, ld_agg, agg_hi + (size_t)R * D, agg_lo ? agg_lo + (size_t)R * D : nullptr, ld_agg, x, support,
                                 end_points, cat_indptr, R, n_dst, n_nb, nnz, D, plan, plan_chunk, partial, stream);
 }
 

@@ -21,6 +21,7 @@ import torch.nn as nn
 
 from . import _lib, seg_op
 from ._lib import check
+from . import graph as _graph
 from .graph import _gemm_tf32x3, _sm_count, _split_tf32
 from .seg_op import _p, _stream
 
@@ -46,7 +47,10 @@ class _FusedDense(torch.autograd.Function):
         ldk = (K + 3) // 4 * 4
         x_hi = x_lo = None
         if n > 0:
-            x_hi, x_lo = _split_tf32(x, ldk)
+            if _graph._raw_ok(x):              # plain fp32 operand, split inside the kernel
+                x_hi = x
+            else:
+                x_hi, x_lo = _split_tf32(x, ldk)
             w_hi, w_lo = _split_tf32(weight, ldk)
             _gemm_tf32x3(out, x_hi, x_lo, w_hi, w_lo, n, N, K, epilogue=0 if slope == 1.0 else 1, slope=slope,
                          bias=bias)
@@ -72,7 +76,8 @@ class _FusedDense(torch.autograd.Function):
         gout = gout.contiguous()
         ldz = (N + 3) // 4 * 4
         gz_hi = torch.empty((n, ldz), dtype=torch.float32, device=dev)
-        gz_lo = torch.empty_like(gz_hi)
+        # x_lo None = the forward took x raw; gZ then goes raw as well (a raw B operand needs a raw A)
+        gz_lo = None if x_lo is None else torch.empty_like(gz_hi)
         check(lib.sg_act_bwd_split(_p(gz_hi), _p(gz_lo), ldz, _p(gout), _p(out), n, N, ctypes.c_float(ctx.slope),
                                    _stream()), "sg_act_bwd_split")
         if ctx.needs_input_grad[0]:

@@ -20,10 +20,13 @@ from ._lib import check
 from .seg_op import DEFAULT_CHUNK, Schedule, _bytes, _p, _stream
 
 
-def _as_np(a, dtype):
+def _as_tensor(a, dtype):
+    """numpy array / torch tensor (any device) -> 1-D torch tensor of ``dtype``; no device round trip."""
     if isinstance(a, torch.Tensor):
-        a = a.detach().cpu().numpy()
-    return np.ascontiguousarray(a, dtype=dtype)
+        t = a.detach()
+        return t if t.dtype == dtype else t.to(dtype)
+    np_dtype = {torch.int32: np.int32, torch.float32: np.float32}[dtype]
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype))
 
 
 class MultiLinkCSR:
@@ -34,37 +37,70 @@ class MultiLinkCSR:
     ``support_l[r]`` is the edge normalisation 1/sqrt(d_i d_j).  Levels without edges may
     arrive as the reference's length-1 dummies (``empty_as_zero``, graph.py:221-222): only
     the first ``indptr_l[r][-1]`` entries of each list are used.
+
+    The lists may be numpy arrays, (pinned) CPU tensors or CUDA tensors.  Each level is copied ONCE, straight
+    into its slice of the concatenated device arrays (asynchronously from pinned memory), and the concatenated
+    indptr is assembled on the device — no host-side concatenation and no device->host transfer.  The only
+    host-side value needed is the edge count of every level: read from the host ``indptr_l`` for free, or given
+    as ``nnz_l`` when the lists already live on the device (otherwise ONE stacked device->host read).
+    ``validate=True`` additionally checks the index ranges on the device and raises (that check synchronises).
     """
 
     def __init__(self, end_points_l, indptr_l, support_l, n_nb, device=None, chunk=DEFAULT_CHUNK,
-                 use_schedule=True):
+                 use_schedule=True, nnz_l=None, validate=False):
         if not (len(end_points_l) == len(indptr_l) == len(support_l)) or len(indptr_l) == 0:
             raise ValueError("end_points_l, indptr_l and support_l must be non-empty lists of equal length")
         if device is None:
             device = next((t.device for t in list(end_points_l) + list(indptr_l)
                            if isinstance(t, torch.Tensor) and t.is_cuda), torch.device("cuda"))
-        self.device = torch.device(device)
-        self.R = len(indptr_l)
-        ptrs = [_as_np(p, np.int32) for p in indptr_l]
-        self.n_dst = int(ptrs[0].shape[0]) - 1
-        if any(p.shape[0] != self.n_dst + 1 for p in ptrs):
+        self.device = dev = torch.device(device)
+        self.R = R = len(indptr_l)
+        ptrs = [_as_tensor(p, torch.int32) for p in indptr_l]
+        self.n_dst = n_dst = int(ptrs[0].shape[0]) - 1
+        if any(p.dim() != 1 or p.shape[0] != n_dst + 1 for p in ptrs):
             raise ValueError("every indptr must have n_dst + 1 entries")
-        self.nnz_l = [int(p[-1]) for p in ptrs]
-        self.nnz = int(sum(self.nnz_l))
+        if R * n_dst >= 2 ** 31:
+            raise ValueError("R * n_dst overflows int32")
+        if nnz_l is None:
+            if all(not p.is_cuda for p in ptrs):
+                nnz_l = [int(p[-1]) for p in ptrs]
+            else:   # device-resident lists without counts: one stacked read (pass nnz_l to avoid it)
+                nnz_l = [int(v) for v in torch.stack([p[-1].to(dev) for p in ptrs]).tolist()]
+        self.nnz_l = [int(n) for n in nnz_l]
+        if len(self.nnz_l) != R or any(n < 0 for n in self.nnz_l):
+            raise ValueError("nnz_l must hold one non-negative edge count per level")
+        self.nnz = nnz = int(sum(self.nnz_l))
         self.n_nb = int(n_nb)
-        eps = [_as_np(e, np.int32)[:n] for e, n in zip(end_points_l, self.nnz_l)]
-        sup = [_as_np(s, np.float32)[:n] for s, n in zip(support_l, self.nnz_l)]
-        offs = np.concatenate([[0], np.cumsum(self.nnz_l)]).astype(np.int64)
-        cat_ptr = np.concatenate([ptrs[0][:1].astype(np.int64)] +
-                                 [ptrs[r][1:].astype(np.int64) + offs[r] for r in range(self.R)])
-        if cat_ptr[-1] != self.nnz or self.R * self.n_dst >= 2 ** 31:
-            raise ValueError("inconsistent indptr lists")
-        ep_cat = np.concatenate(eps) if self.nnz else np.zeros(0, np.int32)
-        if self.nnz and (ep_cat.min() < 0 or ep_cat.max() >= self.n_nb):
-            raise ValueError("end point index out of range of the neighbour feature matrix")
-        self._init_device(torch.from_numpy(ep_cat), torch.from_numpy(np.concatenate(sup) if self.nnz else
-                                                                     np.zeros(0, np.float32)),
-                          torch.from_numpy(cat_ptr.astype(np.int32)), chunk, use_schedule)
+        offs = [0]
+        for n in self.nnz_l:
+            offs.append(offs[-1] + n)
+        ep_cat = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+        sup_cat = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz]
+        ptr2 = torch.empty((R, n_dst + 1), dtype=torch.int32, device=dev)
+        for r in range(R):
+            n = self.nnz_l[r]
+            e, s_ = _as_tensor(end_points_l[r], torch.int32), _as_tensor(support_l[r], torch.float32)
+            if e.shape[0] < n or s_.shape[0] < n:
+                raise ValueError(f"level {r}: indptr ends at {n} but only {min(e.shape[0], s_.shape[0])} edges were given")
+            if n:
+                ep_cat[offs[r]:offs[r + 1]].copy_(e[:n], non_blocking=True)
+                sup_cat[offs[r]:offs[r + 1]].copy_(s_[:n], non_blocking=True)
+            ptr2[r].copy_(ptrs[r], non_blocking=True)
+        # cat_indptr[r * n_dst + i] = offs[r] + indptr_r[i];  the last entry closes the last level
+        offs_dev = torch.tensor(offs[:-1], dtype=torch.int32).to(dev, non_blocking=True)
+        cat_indptr = torch.empty(R * n_dst + 1, dtype=torch.int32, device=dev)
+        cat_indptr[:R * n_dst].view(R, n_dst).copy_(ptr2[:, :n_dst] + offs_dev[:, None])
+        cat_indptr[R * n_dst:].fill_(nnz)
+        if validate:
+            bad_ptr = (ptr2[:, 0] != 0).any() | (ptr2[:, 1:] < ptr2[:, :-1]).any() | \
+                (ptr2[:, -1] != torch.tensor(self.nnz_l, dtype=torch.int32).to(dev)).any()
+            bad_ep = ((ep_cat < 0) | (ep_cat >= self.n_nb)).any() if nnz else torch.zeros((), dtype=torch.bool, device=dev)
+            flags = torch.stack([bad_ptr, bad_ep]).tolist()
+            if flags[0]:
+                raise ValueError("inconsistent indptr lists")
+            if flags[1]:
+                raise ValueError("end point index out of range of the neighbour feature matrix")
+        self._init_device(ep_cat, sup_cat, cat_indptr, chunk, use_schedule)
 
     @classmethod
     def from_device(cls, end_points, support, cat_indptr, R, n_dst, n_nb, chunk=DEFAULT_CHUNK, use_schedule=True):
@@ -211,7 +247,20 @@ def _split_tf32(src, ld_dst, transpose=False):
     return hi, lo
 
 
+# True: the large activation operands (agg, gZ, Dense inputs) go to the GEMM as plain fp32 and are split into
+# their TF32 hi/lo parts inside the kernel; False: a producer pass writes both halves to HBM first (round-1 path,
+# kept for A/B measurements and as the fallback for operands whose row stride is not a multiple of 4 floats).
+GEMM_INKERNEL_SPLIT = True
+
+
+def _raw_ok(t):
+    """Can ``t`` be a raw (plain fp32) TMA operand: 2-D, unit inner stride, 16-byte aligned rows."""
+    return (GEMM_INKERNEL_SPLIT and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0)
+
+
 def _gemm_tf32x3(D, a_hi, a_lo, b_hi, b_lo, M, N, K, mn_major=False, epilogue=0, slope=0.0, splits=1, bias=None):
+    """a_lo / b_lo None: that operand is plain fp32 and is split inside the kernel."""
     lib = _lib.load()
     ws = None
     if splits > 1:
@@ -251,7 +300,7 @@ class _FusedAggTransform(torch.autograd.Function):
         ld = (Kx + 31) // 32 * 32
         dev = x.device
         agg_hi = torch.empty((max(n_dst, 1), ld), dtype=torch.float32, device=dev)
-        agg_lo = torch.empty_like(agg_hi)
+        agg_lo = None if GEMM_INKERNEL_SPLIT else torch.empty_like(agg_hi)     # None: agg_hi holds plain fp32
         sched = csr.schedule()
         if sched is not None:
             part = sched.partial(1, D, extra_per_row=1)
@@ -270,6 +319,7 @@ class _FusedAggTransform(torch.autograd.Function):
             _gemm_tf32x3(out, agg_hi, agg_lo, w_hi, w_lo, n_dst, U, Kx, epilogue=1, slope=slope)
             _prof_end("gemm_fwd", e0, csr)
         ctx.csr, ctx.slope, ctx.dims = csr, slope, (n_nb, D, R, n_dst, U, Kx, ld)
+        ctx.raw = agg_lo is None
         ctx.save_for_backward(agg_hi, agg_lo, out, w_ext)
         return out
 
@@ -283,7 +333,7 @@ class _FusedAggTransform(torch.autograd.Function):
         gout = gout.contiguous()
         ldz = (U + 3) // 4 * 4
         gz_hi = torch.empty((max(n_dst, 1), ldz), dtype=torch.float32, device=dev)
-        gz_lo = torch.empty_like(gz_hi)
+        gz_lo = None if ctx.raw else torch.empty_like(gz_hi)
         check(lib.sg_act_bwd_split(_p(gz_hi), _p(gz_lo), ldz, _p(gout), _p(out), n_dst, U, ctypes.c_float(slope),
                                    _stream()), "sg_act_bwd_split")
         gx = gw = None

@@ -17,13 +17,19 @@ Set ``reference_order=True`` to run the reference's operator order through the p
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch.nn.modules.lazy import LazyModuleMixin
 
 from .. import seg_op
 from ..graph import FUSED_DIMS, MultiLinkCSR, fused_agg_transform, multilink_aggregate, pack_w_ext
 from .common import activation_code, get_activation, xavier_in_uniform_
 
 
-class BaseAggregator(nn.Module):
+class BaseAggregator(LazyModuleMixin, nn.Module):
+    cls_to_become = None
+
+    def initialize_parameters(self, *args, **kwargs):   # aggregators without deferred shapes
+        pass
+
     @property
     def use_mulit_link(self):  # (sic) spelled as in the reference, aggregators.py:9
         raise NotImplementedError
@@ -75,12 +81,19 @@ class MultiLinkGCNAggregator(BaseAggregator):
     def use_edge_type(self):
         return False
 
+    def initialize_parameters(self, neighbor_data, *args, **kwargs):
+        """torch lazy-module protocol: shapes come from the first input (MXNet deferred init); state_dict() /
+        load_state_dict() work before that (load materialises from the checkpoint's shapes)."""
+        if self.has_uninitialized_params():
+            self._materialize(neighbor_data.shape[-1], neighbor_data.device)
+
     def _materialize(self, in_units, device):
         for i in range(self._num_links):
             w, b = getattr(self, f"weight{i}"), getattr(self, f"bias{i}")
             if isinstance(w, nn.UninitializedParameter):
                 w.materialize((self._units, in_units), device=device, dtype=torch.float32)
                 xavier_in_uniform_(w, in_units)
+            if isinstance(b, nn.UninitializedParameter):
                 b.materialize((self._units,), device=device, dtype=torch.float32)
                 with torch.no_grad():
                     b.zero_()
@@ -100,24 +113,30 @@ class MultiLinkGCNAggregator(BaseAggregator):
         return ws, bs
 
     def _plan(self, neighbor_rows, end_points_l, indptr_l, support_l):
+        """Device plan of the three per-level lists.  Torch tensors are cached by identity AND version of every
+        tensor (an in-place update of any of them rebuilds the plan); numpy inputs cannot be watched for in-place
+        changes, so they are uploaded on every call — as the reference does (layers.py:366-377)."""
         if isinstance(end_points_l, MultiLinkCSR):
             return end_points_l
-        key = tuple(id(t) for t in list(end_points_l) + list(indptr_l) + list(support_l))
+        tensors = list(end_points_l) + list(indptr_l) + list(support_l)
+        if not all(isinstance(t, torch.Tensor) for t in tensors):
+            return MultiLinkCSR(end_points_l, indptr_l, support_l, neighbor_rows)
+        key = tuple(id(t) for t in tensors) + (int(neighbor_rows),)
+        versions = [t._version for t in tensors]
         hit = self._plan_cache.get(key)
-        if hit is not None and hit[0] == [getattr(t, "_version", 0) for t in end_points_l]:
+        if hit is not None and hit[0] == versions:
             return hit[1]
         csr = MultiLinkCSR(end_points_l, indptr_l, support_l, neighbor_rows)
-        if len(self._plan_cache) > 16:
-            self._plan_cache.clear()
+        if len(self._plan_cache) >= 4:           # a plan holds ~40 B per edge of derived arrays: keep few
+            self._plan_cache.pop(next(iter(self._plan_cache)))
         # keep the keyed tensors alive so ids cannot be recycled
-        self._plan_cache[key] = ([getattr(t, "_version", 0) for t in end_points_l], csr,
-                                 (end_points_l, indptr_l, support_l))
+        self._plan_cache[key] = (versions, csr, tensors)
         return csr
 
     def forward(self, neighbor_data, end_points_l, indptr_l=None, support_l=None):
         """neighbor_data (N_nb, D); the three lists as in aggregators.py:111-128 — or a prebuilt
         :class:`MultiLinkCSR` in place of ``end_points_l``."""
-        if isinstance(getattr(self, "weight0"), nn.UninitializedParameter):
+        if self.has_uninitialized_params():
             self._materialize(neighbor_data.shape[-1], neighbor_data.device)
         neighbor_data = self.dropout(neighbor_data)
         ws, bs = self._effective_params()

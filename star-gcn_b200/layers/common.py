@@ -11,6 +11,7 @@ import math
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch.nn.modules.lazy import LazyModuleMixin
 
 
 class IdentityActivation(nn.Module):
@@ -70,34 +71,44 @@ def xavier_in_uniform_(weight, fan_in):
     return weight
 
 
-class Dense(nn.Module):
-    """y = x W^T + b with W (units, in_units); in_units inferred at first call (deferred init)."""
+class Dense(LazyModuleMixin, nn.Module):
+    """y = x W^T + b with W (units, in_units); in_units inferred at first call (MXNet's deferred init).
+
+    Until then ``weight`` / ``bias`` are registered ``UninitializedParameter`` s (torch's lazy-module protocol):
+    ``state_dict()`` works on a freshly built model and ``load_state_dict()`` materialises them from the
+    checkpoint's shapes — the counterpart of gluon's ``load_parameters`` on a deferred-init block."""
+
+    cls_to_become = None
 
     def __init__(self, units, in_units=None, use_bias=True, device=None):
         super().__init__()
         self._units = units
         self._use_bias = use_bias
-        self.weight = nn.UninitializedParameter() if in_units is None else None
-        self.bias = None
+        self.weight = nn.UninitializedParameter()
+        if use_bias:
+            self.bias = nn.UninitializedParameter()
+        else:
+            self.register_parameter("bias", None)
         if in_units is not None:
             self._materialize(in_units, device)
 
     def _materialize(self, in_units, device):
-        w = torch.empty((self._units, in_units), dtype=torch.float32, device=device)
-        xavier_in_uniform_(w, in_units)
         if isinstance(self.weight, nn.UninitializedParameter):
             self.weight.materialize((self._units, in_units), device=device, dtype=torch.float32)
+            xavier_in_uniform_(self.weight, in_units)
+        if self._use_bias and isinstance(self.bias, nn.UninitializedParameter):
+            self.bias.materialize((self._units,), device=device, dtype=torch.float32)
             with torch.no_grad():
-                self.weight.copy_(w)
-        else:
-            self.weight = nn.Parameter(w)
-        if self._use_bias:
-            self.bias = nn.Parameter(torch.zeros(self._units, dtype=torch.float32, device=device))
+                self.bias.zero_()
+
+    def initialize_parameters(self, x, *args, **kwargs):
+        if self.has_uninitialized_params():
+            self._materialize(x.shape[-1], x.device)
 
     def forward(self, x, act=None):
         """x W^T + b on the tcgen05 GEMM; ``act`` in {None, 'leaky', 'relu'} rides in its epilogue."""
         from ..decoder import fused_dense
-        if isinstance(self.weight, nn.UninitializedParameter):
+        if self.has_uninitialized_params():       # direct call that bypassed the lazy pre-hook
             self._materialize(x.shape[-1], x.device)
         lead = x.shape[:-1]
         y = fused_dense(x.reshape(-1, x.shape[-1]), self.weight, self.bias, act)

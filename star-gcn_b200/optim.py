@@ -21,6 +21,9 @@ class FusedAdam:
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FusedAdam needs at least one parameter")
+        if any(isinstance(p, torch.nn.UninitializedParameter) for p in self.params):
+            raise ValueError("FusedAdam: a parameter is still uninitialised (deferred shape) — run one forward pass "
+                             "or load a checkpoint before building the optimiser")
         for p in self.params:
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise ValueError("FusedAdam handles contiguous float32 CUDA parameters only")
@@ -36,6 +39,7 @@ class FusedAdam:
         self._numels = torch.tensor([p.numel() for p in self.params], dtype=torch.int64, device=dev)
         self._ptr = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=dev)
         self._p_ptrs, self._m_ptrs, self._v_ptrs = self._ptr(self.params), self._ptr(self.m), self._ptr(self.v)
+        self._p_key = tuple(p.data_ptr() for p in self.params)
         self._g_ptrs, self._g_key = None, None
         self._ws = torch.empty(max(self.n_work, 1), dtype=torch.float32, device=dev)
         self._norm = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -49,6 +53,14 @@ class FusedAdam:
         self.lr = lr
 
     def _grad_table(self):
+        # parameters that were moved / re-materialised since the last step (model.to(...), load_state_dict into new
+        # storage): refresh the pointer table instead of updating stale memory
+        p_key = tuple(p.data_ptr() for p in self.params)
+        if p_key != self._p_key:
+            for p, m in zip(self.params, self.m):
+                if p.shape != m.shape or p.device != m.device:
+                    raise RuntimeError("FusedAdam: a parameter changed shape or device after the optimiser was built")
+            self._p_ptrs, self._p_key = self._ptr(self.params), p_key
         grads = []
         for p in self.params:
             if p.grad is None:

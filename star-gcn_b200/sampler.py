@@ -43,6 +43,7 @@ class DeviceCSR:
         self.n_cols = int(n_cols)
         self.nnz = self.end_points.numel()
         self.R = self.multi_link.numel()
+        self._calls = 0              # advances with every sampling call that does not pass its own seed
         if support is not None:
             self.support = _dev_f32(support, self.device)
         else:
@@ -84,9 +85,20 @@ class DeviceCSR:
         return DeviceCSR(new_ptr, new_ep, new_val, self.multi_link, self.n_cols, row_degrees=row_deg.contiguous(),
                          col_degrees=col_degrees, symm=symm, device=dev)
 
-    def sample_positions(self, src_inds=None, num_neighbors=-1, seed=0):
-        """random_sample_fix_neighbor: (sampled positions on the nnz axis, dst_ind_ptr) as device tensors."""
+    def _next_seed(self, seed):
+        """``seed=None`` draws a fresh stream per call (the reference's mt19937 engines advance across calls,
+        graph_sampler.cpp:742-779); an explicit seed makes the sample a pure function of (seed, row, draw)."""
+        if seed is not None:
+            return int(seed)
+        self._calls += 1
+        return (self._calls * 0x9E3779B97F4A7C15 + 0x1234567) & (2 ** 64 - 1)
+
+    def sample_positions(self, src_inds=None, num_neighbors=-1, seed=None):
+        """random_sample_fix_neighbor: (sampled positions on the nnz axis, dst_ind_ptr) as device tensors.
+        Fan-outs above 256 per row are rejected by the kernel (its per-row pool lives in shared memory); the
+        shipped configurations use -1 (all neighbours)."""
         lib = _lib.load()
+        seed = self._next_seed(seed)
         sel = None if src_inds is None else _dev_i32(src_inds, self.device)
         n_sel = self.n_rows if sel is None else sel.numel()
         k = -1 if num_neighbors is None else int(num_neighbors)
@@ -123,7 +135,7 @@ class DeviceCSR:
             raise ValueError("an edge value is not in multi_link (graph_sampler.cpp:303 ASSERT)")
         return cat_indptr, ep_cat, sup_cat, split_index, val_cat
 
-    def sample_neighbors(self, src_inds=None, num_neighbors=-1, seed=0):
+    def sample_neighbors(self, src_inds=None, num_neighbors=-1, seed=None):
         """CSRMat.sample_neighbors(use_multi_link=True) -> MultiLinkCSR over the selected rows.
         End points are column INDICES of this matrix (the reference maps them to node ids and
         gen_plan maps those back to local indices; with every column present the two coincide)."""

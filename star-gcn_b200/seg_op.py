@@ -79,14 +79,13 @@ class Schedule:
         self.partial_rows = int(lib.sg_plan_partial_rows(self.n_seg, self.nnz, self.chunk))
         check(lib.sg_plan_build(_p(self.buf), nbytes, _p(indptr), self.n_seg, self.nnz, self.chunk, _stream()),
               "sg_plan_build")
-        self._partial = None
 
     def partial(self, K, F, extra_per_row=0):
-        """Scratch for the partial rows of split segments (cached, grown on demand)."""
+        """Scratch for the partial rows of split segments.  Taken from the caching allocator on EVERY call, so
+        two streams that use the same pattern concurrently never share it (the allocator hands a block to
+        another stream only after the kernels that used it have finished)."""
         need = K * self.partial_rows * (F + extra_per_row)
-        if self._partial is None or self._partial.numel() < need:
-            self._partial = torch.empty(max(need, 4), dtype=torch.float32, device=self.buf.device)
-        return self._partial
+        return torch.empty(max(need, 4), dtype=torch.float32, device=self.buf.device)
 
 
 class CSRPattern:
@@ -142,6 +141,11 @@ class CSRPattern:
 
 _PATTERN_CACHE = OrderedDict()
 _PATTERN_CACHE_MAX = 64
+_PATTERN_CACHE_MAX_BYTES = 1 << 30      # derived arrays (transpose + schedules) cost ~40 B per edge
+
+
+def _pattern_bytes(pat):
+    return 40 * pat.nnz + 24 * (pat.n_seg + pat.n_nb)
 
 
 def get_pattern(indices, indptr, n_nb):
@@ -157,7 +161,8 @@ def get_pattern(indices, indptr, n_nb):
     pat = CSRPattern(indices, indptr, n_nb)
     try:
         _PATTERN_CACHE[key] = (weakref.ref(indices), weakref.ref(indptr), pat)
-        while len(_PATTERN_CACHE) > _PATTERN_CACHE_MAX:
+        while len(_PATTERN_CACHE) > 1 and (len(_PATTERN_CACHE) > _PATTERN_CACHE_MAX or
+                                           sum(_pattern_bytes(v[2]) for v in _PATTERN_CACHE.values()) > _PATTERN_CACHE_MAX_BYTES):
             _PATTERN_CACHE.popitem(last=False)
     except TypeError:
         pass
@@ -395,9 +400,21 @@ class _SegSoftmax(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # public operators (names / keywords of mx.nd.contrib.seg_*)
 # --------------------------------------------------------------------------------------------
+def _chk_seg_shapes(indptr, rhs=None, lhs=None):
+    """Shape relations the reference's shape inference enforces (seg_op.h:255-319): indptr has n_seg + 1 >= 1
+    entries, ``rhs`` is (batch, n_seg) and ``lhs`` (batch, nnz) with the same batch."""
+    if indptr.numel() < 1:
+        raise ValueError("indptr must have at least one element")
+    if rhs is not None and rhs.shape[1] != indptr.numel() - 1:
+        raise ValueError(f"per-segment operand has {rhs.shape[1]} columns but indptr describes {indptr.numel() - 1} segments")
+    if lhs is not None and rhs is not None and lhs.shape[0] != rhs.shape[0]:
+        raise ValueError(f"batch sizes differ: {lhs.shape[0]} vs {rhs.shape[0]}")
+
+
 def seg_sum(data, indptr, out=None, req="write"):
     """ret[b, i] = sum(data[b, indptr[i]:indptr[i+1]])   (seg_ops_cuda/README.md:5-22)"""
     data, indptr = _chk_float(data, "data", 2), _chk_int(indptr, "indptr")
+    _chk_seg_shapes(indptr)
     if out is not None or req != "write":
         return _seg_reduce(data, indptr, "sum", out, req)
     return _SegSum.apply(data, indptr)
@@ -405,21 +422,27 @@ def seg_sum(data, indptr, out=None, req="write"):
 
 def seg_broadcast_add(lhs, rhs, indptr):
     lhs, rhs, indptr = _chk_float(lhs, "lhs", 2), _chk_float(rhs, "rhs", 2), _chk_int(indptr, "indptr")
+    _chk_seg_shapes(indptr, rhs, lhs)
     return _SegBroadcast.apply(lhs, rhs, indptr, "add")
 
 
 def seg_broadcast_mul(lhs, rhs, indptr):
     lhs, rhs, indptr = _chk_float(lhs, "lhs", 2), _chk_float(rhs, "rhs", 2), _chk_int(indptr, "indptr")
+    _chk_seg_shapes(indptr, rhs, lhs)
     return _SegBroadcast.apply(lhs, rhs, indptr, "mul")
 
 
 def seg_broadcast_to(data, indptr, nnz):
     data, indptr = _chk_float(data, "data", 2), _chk_int(indptr, "indptr")
+    _chk_seg_shapes(indptr, data)
+    if int(nnz) < 0:
+        raise ValueError("nnz must be non-negative")
     return _SegBroadcastTo.apply(data, indptr, int(nnz))
 
 
 def seg_softmax(data, indptr):
     data, indptr = _chk_float(data, "data", 2), _chk_int(indptr, "indptr")
+    _chk_seg_shapes(indptr)
     return _SegSoftmax.apply(data, indptr)
 
 

@@ -13,6 +13,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _gemm_operand_path():
+    """SGTEST_PRESPLIT=1 runs the whole suite on the round-1 GEMM operand path (activations pre-split in HBM) —
+    a test-harness switch for A/B runs; the library itself reads no environment variables."""
+    if os.environ.get("SGTEST_PRESPLIT") == "1":
+        import stargcn_b200  # noqa: F401
+        from stargcn_b200 import graph
+        graph.GEMM_INKERNEL_SPLIT = False
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

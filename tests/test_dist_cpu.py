@@ -107,3 +107,29 @@ def test_halo_plan_single_rank_is_identity():
     assert np.array_equal(plan.local_cols, cols.astype(np.int32))
     with pytest.raises(ValueError):
         sgd.HaloPlan(np.array([5]), np.array([0, 4]), 0, 1)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_strong_partition_covers_the_graph_once(world):
+    """bench.partition_sides(scaling='strong'): the nnz-balanced node ranges tile both sides, the per-rank CSR slices
+    put together are the whole graph, and the per-rank edge counts are balanced ('balanced by nnz')."""
+    import bench
+    from stargcn_b200 import synth
+    base = synth.make_bipartite(400, 150, 9000, n_levels=5, seed=2)
+    for side, key in (("user", "u2i"), ("item", "i2u")):
+        rows, edges, los = 0, [], []
+        for rank in range(world):
+            ps = bench.partition_sides(base, rank, world, "strong")[side]
+            indptr, cols, vals, sup = ps["csr"]
+            assert indptr[0] == 0 and indptr[-1] == cols.size == vals.size == sup.size
+            assert ps["n_dst"] == len(indptr) - 1
+            lo = ps["dst_lo"]
+            p0 = base[key]["indptr"][lo]
+            assert np.array_equal(cols, base[key]["cols"][p0:p0 + cols.size])
+            assert np.array_equal(sup, base[key]["support"][p0:p0 + cols.size])
+            assert ps["nb_ranges"][0] == 0 and ps["nb_ranges"][-1] == (base["n_item"] if side == "user" else base["n_user"])
+            rows += ps["n_dst"]; edges.append(int(cols.size)); los.append(lo)
+        assert rows == (base["n_user"] if side == "user" else base["n_item"])
+        assert sum(edges) == base["nnz"] and los == sorted(los)
+        max_deg = int(np.diff(base[key]["indptr"]).max())
+        assert max(edges) - min(edges) <= 2 * max_deg + 1      # balanced up to one row's worth of edges per cut

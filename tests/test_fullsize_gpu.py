@@ -1,7 +1,10 @@
 """BASELINE.json configs at their full sizes.
 
 ML-1M shape (config 3): direct comparison with the reference-order oracle (finishes in seconds).
-ML-10M shape (config 4, the benchmark workload): size-independent properties of the fused path —
+ML-10M shape (config 4, the benchmark workload): (i) the reference-order oracle on a row sample of BOTH
+directions (2 000 user rows / 300 item rows, always including the 20 highest-degree nodes, whose item-side
+segments are cut into hundreds of partial rows): forward rows, the data gradient on every touched row and every
+dW_r / db_r, at 1e-5; (ii) size-independent properties of the fused path —
   adjointness  <A x, g> == <x, A^T g>   (the backward gather is the exact transpose of the forward one)
   linearity    A(a x + b y) == a A x + b A y   (identity activation, zero bias)
   support sums wsum == segment sums of the support array (checked through the bias term)
@@ -23,11 +26,20 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def build(shape, act, seed=0, zero_bias=False):
+_WL = {}
+
+
+def layer_inputs(shape):
     from stargcn_b200 import synth
+    if shape not in _WL:
+        _WL[shape] = synth.make_layer_inputs(shape, seed=1000)
+    return _WL[shape]
+
+
+def build(shape, act, seed=0, zero_bias=False):
     from stargcn_b200.graph import MultiLinkCSR
     from stargcn_b200.layers import MultiLinkGCNAggregator
-    wl = synth.make_layer_inputs(shape, seed=1000)
+    wl = layer_inputs(shape)
     R, D = wl["R"], wl["D"]
     rs = np.random.RandomState(seed)
     bound = np.sqrt(3.0 / D)
@@ -61,6 +73,71 @@ def test_ml1m_shape_vs_oracle():
     assert rel_err(xd.grad.cpu().numpy(), gx_ref) <= TOL
     assert rel_err(agg.weight1.grad.cpu().numpy(), gw_ref[1]) <= TOL
     assert rel_err(agg.bias4.grad.cpu().numpy(), gb_ref[4]) <= TOL
+
+
+def sub_lists(lists, rows):
+    """Per-level CSR lists restricted to the destination rows ``rows`` (column ids stay global)."""
+    ep_l, ptr_l, sup_l = lists[:3]
+    out_e, out_p, out_s = [], [], []
+    for e, p, s in zip(ep_l, ptr_l, sup_l):
+        p64 = p.astype(np.int64)
+        lens = p64[rows + 1] - p64[rows]
+        sub_ptr = np.concatenate([[0], np.cumsum(lens)])
+        pos = np.repeat(p64[rows] - sub_ptr[:-1], lens) + np.arange(sub_ptr[-1])
+        out_e.append(np.ascontiguousarray(e[pos], np.int32))
+        out_s.append(np.ascontiguousarray(s[pos], np.float32))
+        out_p.append(sub_ptr.astype(np.int32))
+    return out_e, out_p, out_s
+
+
+@pytest.mark.parametrize("side", ["user", "item"])
+def test_ml10m_rows_vs_oracle(side):
+    """The benchmark workload itself against the reference-order oracle (test_seg_ops.py:380-443 is the
+    reference's own big-shape check; this is the same comparison on the ML-10M-shaped layer).  The upstream
+    gradient is non-zero only on the sampled destination rows, so the FULL data gradient and every weight /
+    bias gradient of the device run equal the oracle's on the sub-CSR of those rows."""
+    from stargcn_b200.graph import MultiLinkCSR
+    from stargcn_b200.layers import MultiLinkGCNAggregator
+    wl = layer_inputs("ml-10m")
+    R, D = wl["R"], wl["D"]
+    lists = wl[side]
+    x = wl["x_item"] if side == "user" else wl["x_user"]
+    n_dst = wl["n_user"] if side == "user" else wl["n_item"]
+    deg = sum(np.diff(p.astype(np.int64)) for p in lists[1])
+    rs = np.random.RandomState(11)
+    top = np.argsort(-deg, kind="stable")[:20]
+    rest = rs.choice(n_dst, 2000 if side == "user" else 280, replace=False)
+    rows = np.unique(np.concatenate([top, rest])).astype(np.int64)
+    ep_s, ptr_s, sup_s = sub_lists(lists, rows)
+    bound = np.sqrt(3.0 / D)
+    ws = [rs.uniform(-bound, bound, (U, D)).astype(np.float32) for _ in range(R)]
+    bs = [rs.uniform(-0.1, 0.1, U).astype(np.float32) for _ in range(R)]
+    ref_out, pre = orl.multilink_aggregator_forward(x, ws, bs, ep_s, ptr_s, sup_s, "sum", "leaky")
+
+    csr = MultiLinkCSR(lists[0], lists[1], lists[2], n_nb=x.shape[0], device="cuda")
+    agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", ordinal_sharing=False, accum="sum", in_units=D).cuda()
+    with torch.no_grad():
+        for i in range(R):
+            getattr(agg, f"weight{i}").copy_(dev(ws[i]))
+            getattr(agg, f"bias{i}").copy_(dev(bs[i]))
+    xd = dev(x).requires_grad_(True)
+    out = agg(xd, csr)
+    got = out.detach()[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert rel_err(got, ref_out) <= TOL
+    if side == "item":   # the hottest items really are split into many partial rows at this size
+        assert int(deg[top[0]]) > 50 * 256
+    near = np.abs(pre) <= 1e-5 * np.abs(pre).max()
+    assert (near & (pre != 0)).mean() < 1e-3
+    pre = np.where(near, np.where(got > 0, np.abs(pre) + 1e-30, -np.abs(pre) - 1e-30), pre).astype(np.float32)
+    g_rows = rs.normal(size=(len(rows), U)).astype(np.float32)
+    gx_ref, gw_ref, gb_ref = orl.multilink_aggregator_backward(x, ws, bs, ep_s, ptr_s, sup_s, g_rows, pre, "sum", "leaky")
+    gout = torch.zeros((n_dst, U), device="cuda")
+    gout[torch.from_numpy(rows).cuda()] = dev(g_rows)
+    out.backward(gout)
+    assert rel_err(xd.grad.cpu().numpy(), gx_ref) <= TOL
+    for r in range(R):
+        assert rel_err(getattr(agg, f"weight{r}").grad.cpu().numpy(), gw_ref[r]) <= TOL, r
+        assert rel_err(getattr(agg, f"bias{r}").grad.cpu().numpy(), gb_ref[r]) <= TOL, r
 
 
 @pytest.fixture(scope="module")

@@ -3,7 +3,9 @@ input embeddings, reconstruction decoder and rating head, D=64 — assembled by 
 against a torch-CPU fp64 execution of the SAME plans with plain dense/index ops in the reference's operator
 order (per level FullyConnected, weighted segment sum, add_n, LeakyReLU; Dense; take; losses).
 
-The loss agrees to 1e-5.  Gradient bars are explained where they are applied."""
+The loss agrees to 1e-5.  Every parameter gradient is held to 2e-5 + 2x the fp32 reference execution's own
+distance from the fp64 answer; LeakyReLU branches inside the fp32 rounding band around 0 are taken from the
+device forward (the same pinning as tests/test_layers_gpu.py:pin_kink), nothing else is relaxed."""
 import numpy as np
 import pytest
 import torch
@@ -22,12 +24,55 @@ def vec_err(got, want):
     return l2, cos
 
 
-def leaky(z, act):
-    return torch.where(z > 0, z, 0.1 * z) if act == "leaky" else z
+class BranchLog:
+    """Activation outputs of the device forward, in call order (aggregator, output Dense, first Dense of an
+    embed map), recorded by forward hooks; the oracle replays them to pin LeakyReLU branches."""
+
+    def __init__(self, model):
+        self.outs, self.handles = [], []
+        mods = []
+        for enc in model.encoders:
+            layer = enc[0]
+            mods += list(layer.aggregators._mods) + list(layer._out_fcs._mods)
+        for maps in model.embed_maps:
+            mods += [m.l0 for m in maps._mods]
+        for m in mods:
+            self.handles.append(m.register_forward_hook(lambda mod, inp, out: self.outs.append(out.detach().cpu())))
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
 
 
-def oracle(model, plans, lookups, needed, noise, recon_ids, gt_ratings, act, lam, dt=torch.float64):
+def make_leaky(act, log=None, band=1e-5):
+    """LeakyReLU(0.1) whose branch inside |z| <= band * max|z| follows the device forward (pin_kink)."""
+    it = iter(log) if log is not None else None
+    pinned = [0, 0]
+
+    def leaky(z):
+        if act != "leaky":
+            if it is not None:
+                next(it)
+            return z
+        pos = z > 0
+        if it is not None:
+            dev_out = next(it)
+            assert dev_out.shape == z.shape, (dev_out.shape, z.shape)
+            near = z.detach().abs() <= band * z.detach().abs().max()
+            pos = torch.where(near, dev_out > 0, pos)
+            pinned[0] += int((near & (z.detach() != 0)).sum())
+            pinned[1] += z.numel()
+        return torch.where(pos, z, 0.1 * z)
+    leaky.pinned = pinned
+    return leaky
+
+
+def oracle(model, plans, lookups, needed, noise, recon_ids, gt_ratings, act, lam, dt=torch.float64, log=None):
     """CPU re-execution in ``dt``; parameters are leaf copies so that autograd yields reference gradients."""
+    leaky_fn = make_leaky(act, log)
+
+    def leaky(z, _act):
+        return leaky_fn(z)
     P = {n: p.detach().to(dt).cpu().requires_grad_(True) for n, p in model.named_parameters()}
     i64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64)
 
@@ -84,6 +129,8 @@ def oracle(model, plans, lookups, needed, noise, recon_ids, gt_ratings, act, lam
     loss = sum((0.5 * (p - y) ** 2).mean() for p in pred_r)
     loss = loss + lam * sum(((gt[k] - pe[k]) ** 2).sum(-1).mean() for pe in pred_e for k in pe)
     loss.backward()
+    if log is not None:
+        assert leaky_fn.pinned[0] <= 1e-3 * max(leaky_fn.pinned[1], 1), leaky_fn.pinned   # the pinned set stays tiny
     return float(loss), {n: (p.grad.double() if p.grad is not None else None) for n, p in P.items()}
 
 
@@ -128,7 +175,10 @@ def test_full_stargcn_two_blocks_with_reconstruction(shape, setting, act):
                     out_units=O, n_blocks=2, mid_map=DM, agg_accum="sum", act=act).cuda()
     fan = {("user", "item"): -1, ("item", "user"): -1}
     mean, std, lam = float(ratings.mean()), float(ratings.std()), 0.1
-    pr, pe, gt = model(graph, pairs, noise, recon, fan)               # materialises the lazily-shaped layers
+    model(graph, pairs, noise, recon, fan)                            # materialises the lazily-shaped layers
+    log = BranchLog(model)
+    pr, pe, gt = model(graph, pairs, noise, recon, fan)
+    log.close()
     assert len(pr) == 2 and len(pe) == 2 and pr[0].shape == (B, 1) and pe[1]["item"].shape == (len(recon["item"]), D)
     y = torch.from_numpy(ratings).cuda()
     loss = model.loss(pr, pe, gt, y, mean, std, lam)
@@ -136,15 +186,14 @@ def test_full_stargcn_two_blocks_with_reconstruction(shape, setting, act):
     plans, lookups, needed = model.last_plans
     plans_h = [[(p[0][0], p[0][1])] for p in plans]                   # one depth per block
     target = (ratings - mean) / std
-    ref_loss, ref_g = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam)
-    loss32, g32 = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam, dt=torch.float32)
+    ref_loss, ref_g = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam, log=log.outs)
+    loss32, g32 = oracle(model, plans_h, lookups, needed, noise, recon, target, act, lam, dt=torch.float32, log=log.outs)
     assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
     # Depth compounds rounding (eight GEMM layers, each ~1e-6 from the fp64 answer on the 3xTF32 tensor-core
     # path against ~2e-7 for an fp32 FMA GEMM) and the residual pred - y cancels leading digits, so the bar for
     # the gradients of the WHOLE stack is 2e-5 plus twice the reference-order fp32 execution's own distance from
-    # the fp64 answer.  With LeakyReLU a handful of pre-activations take the other branch (see the module
-    # docstring): there the check is on the gradient as a vector (relative L2 error, direction).
-    checked, errs, bad, flips = 0, {}, [], {}
+    # the fp64 answer — for every parameter, with and without LeakyReLU.
+    checked, errs, bad = 0, {}, []
     for name, p in model.named_parameters():
         if p.grad is None:
             assert ref_g[name] is None or float(ref_g[name].abs().max()) == 0.0, name
@@ -154,34 +203,14 @@ def test_full_stargcn_two_blocks_with_reconstruction(shape, setting, act):
         e_f32 = rel_err(g32[name].numpy().reshape(-1), want.numpy())
         errs[name] = (e_gpu, e_f32)
         checked += 1
-        if act == "identity":
-            if not e_gpu <= 2e-5 + 2 * e_f32:
-                bad.append((name, e_gpu, e_f32))
-        else:
+        if not e_gpu <= 2e-5 + 2 * e_f32:
             l2, cos = vec_err(got, want)
-            if not (l2 <= 5e-3 and cos >= 1 - 1e-5) and ref_g[name].dim() in (1, 2):
-                # One flipped LeakyReLU branch at (node i, unit u) scales gZ[i, u] by 10 and with it row u of
-                # every level's weight / bias gradient of that aggregator — visible where the level's gradient is
-                # small (measured: unit 178 of the Douban-shaped item-side aggregator, relative L2 1.6e-2 on
-                # weight1, every other row inside the bar).  Up to three unit rows may be such flips; the rest
-                # of the parameter must meet the bar.
-                rows = ref_g[name].shape[0]
-                g2, w2 = got.reshape(rows, -1), want.reshape(rows, -1)
-                keep = torch.ones(rows, dtype=torch.bool)
-                keep[torch.topk((g2 - w2).norm(dim=1), min(3, rows - 1)).indices] = False
-                l2, cos = vec_err(g2[keep].reshape(-1), w2[keep].reshape(-1))
-                flips[name] = int((~keep).sum())
-            if not (l2 <= 5e-3 and cos >= 1 - 1e-5):
-                diff = (got - want).abs().reshape(ref_g[name].shape)
-                top = torch.topk(diff.reshape(-1), min(6, diff.numel())).indices
-                where = [tuple(int(v) for v in np.unravel_index(int(t), tuple(diff.shape))) for t in top]
-                bad.append((name, l2, cos, e_gpu, [(w, float(got.reshape(diff.shape)[w]), float(ref_g[name][w])) for w in where]))
+            bad.append((name, e_gpu, e_f32, l2, cos))
     worst = sorted(errs.items(), key=lambda kv: -kv[1][0])[:5]
     print("worst gradient errors (device, fp32 oracle):", worst)
-    print("parameters judged without their (at most 3) worst unit rows:", sorted(flips))
     for b in bad:
         print("OUT OF BAR:", b)
-    assert not bad, [b[:4] for b in bad]
+    assert not bad, bad
     assert checked >= 2 + 2 * (2 * 2 * R + 4 + 8 + 4)                 # tables + per block: agg, out_fc, maps, projs
     # one optimiser step through the multi-tensor clip + Adam with the reference's own hyper-parameters for this
     # config (LR 0.002, GRAD_CLIP 1.0: experiments/cfg/transductive_ml_100k.yml:48,54) keeps everything finite,
