@@ -123,3 +123,24 @@ def test_partitioned_layer_matches_whole_graph(mode):
         assert rel_err(got[r]["gx"], gx_h[r * ni:(r + 1) * ni]) <= TOL      # includes gradients returned by peers
         assert rel_err(got[r]["gw"], agg.weight2.grad.cpu().numpy()) <= TOL   # all-reduced == whole-graph gradient
         assert rel_err(got[r]["gb"], agg.bias2.grad.cpu().numpy()) <= TOL
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the NCCL transport needs two GPUs (run by `gpurun --gpus 2`)")
+def test_partitioned_step_over_nccl_matches_whole_graph():
+    """`bench.py --check` under torchrun: the partitioned step over NCCL (all-to-all and all-gather / reduce-scatter
+    exchange on the weak construction, all-to-all on the nnz-balanced strong partition) against the whole graph."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(torch.cuda.device_count(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                        os.path.join(root, "bench.py"), "--gpus", str(n), "--check"],
+                       capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["ok"] and set(line["cases"]) == {"weak/alltoall", "weak/allgather", "strong/alltoall"}
+    for case in line["cases"].values():
+        assert case["ok"] and max(case["out"], case["gx"], case["gw"], case["gb"]) <= 1e-5

@@ -35,6 +35,8 @@ if [ "${1:-}" != "quick" ]; then
   el "A/B: raw B operand off (K-major GEMMs take pre-split weights — default) vs staged gather"
   timeout 300 python bench.py $BFLAG --no-e2e --no-cpu-baseline --dev gather_variant=1 > $O/bench_staged.json 2> $O/bench_staged.err
   python tools/bench_summary.py < $O/bench_staged.json
+  el "gather sweep: default vs staged (TMA bulk copy) variant"
+  timeout 300 python tools/sweep_gather.py "gather_variant=0" "gather_variant=1" > $O/sweep_gather.log 2>&1; tail -6 $O/sweep_gather.log
   el "A/B: release arrival"
   timeout 300 python bench.py $BFLAG --no-e2e --no-cpu-baseline --dev gemm_arrive=1 > $O/bench_release.json 2> $O/bench_release.err
   python tools/bench_summary.py < $O/bench_release.json

@@ -1,6 +1,9 @@
 """Developer tool: time the four gather launches of one ML-10M-shaped step under tuning knobs, in one process.
-    python tools/sweep_gather.py "SG_GATHER_SHAPE=0" "SG_GATHER_SHAPE=3,SG_GATHER_GRID=24" ...
-Each argument is a comma-separated list of NAME=VALUE environment settings (read by gather.cu on every call)."""
+    python tools/sweep_gather.py "gather_variant=0" "gather_variant=1,gather_grid=24" ...
+Each argument is a comma-separated list of NAME=VALUE development options (sg_dev_option: gather_variant,
+gather_grid); every option is reset to 0 (shipped behaviour) between configurations.  The forward launches write the
+PLAIN fp32 [agg | wsum] operand (the in-kernel-split GEMM's input); results that differ from the first configuration
+are reported with their max abs difference (the staged variant sums in a different order: ~1e-7 relative)."""
 import ctypes
 import os
 import sys
@@ -15,11 +18,11 @@ from stargcn_b200._lib import check  # noqa: E402
 from stargcn_b200.graph import MultiLinkCSR  # noqa: E402
 from stargcn_b200.seg_op import _p, _stream  # noqa: E402
 
-KNOBS = ("SG_GATHER_SHAPE", "SG_GATHER_GRID")
+KNOBS = ("gather_variant", "gather_grid")
 
 
 def main():
-    configs = sys.argv[1:] or ["SG_GATHER_SHAPE=0"]
+    configs = sys.argv[1:] or ["gather_variant=0"]
     wl = bench.load_workload(os.environ.get("SWEEP_WORKLOAD", "ml-10m"))
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -30,7 +33,7 @@ def main():
         x = torch.from_numpy(x_nb).to(dev)
         ld = (R * D + R + 31) // 32 * 32
         agg_hi = torch.empty((csr.n_dst, ld), device=dev)
-        agg_lo = torch.empty_like(agg_hi)
+        agg_lo = None
         gagg = torch.randn((csr.n_dst, R * D), device=dev)
         gx = torch.empty((csr.n_nb, D), device=dev)
         sched, tsched = csr.schedule(), csr.t_schedule()
@@ -69,10 +72,10 @@ def main():
     print(f"{'config':44s} " + " ".join(f"{s[0][:22]}:{d}" for s in sides for d in ("fwd", "bwd")) + "    sum(ms)")
     for cfg in configs:
         for k in KNOBS:
-            os.environ.pop(k, None)
+            _lib.dev_option(k, 0)
         for kv in filter(None, cfg.split(",")):
             k, v = kv.split("=")
-            os.environ[k] = v
+            _lib.dev_option(k, int(v))
         times = []
         for side, fwd, bwd, agg_hi, gx in sides:
             for name, fn, outbuf in (("fwd", fwd, agg_hi), ("bwd", bwd, gx)):
