@@ -785,6 +785,9 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
                           x=torch.from_numpy(sides[side]["x_np"]).pin_memory())
         h2d += sum(t.numel() * t.element_size() for t in ep_l + sup_l + ptr_l + [host[side]["x"]])
 
+    if world == 1:
+        return _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, host, h2d)
+
     # double-buffered prefetch: while step i computes, step i+1's inputs cross PCIe on a copy stream
     # (what a loader thread does); every step still copies all of its inputs inside the timed region
     copy_stream = torch.cuda.Stream(device=dev)
@@ -887,6 +890,127 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
                 "copy overlaps this step's compute), device-side concatenation, device plan rebuild (transpose + schedules), "
                 + ("halo exchange, " if world > 1 else "the two directions on two streams, ") + "fwd+bwd, scalar loss read-back"
                 + ("; per rank, halo index plan reused" if world > 1 else ""))
+
+
+def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, host, h2d):
+    """Single-GPU end-to-end step for same-shaped plans (every training iteration of a full-neighbourhood run): two
+    device slots, each with its OWN pair of MultiLinkCSR plans built once; per step the caller's pinned per-level
+    lists and features are copied into the idle slot on a copy stream (``MultiLinkCSR.load_lists_``), then ONE CUDA
+    graph per slot re-derives the plan (``rebuild_``: schedules + transposed operands, the latter read off the reverse
+    direction's plan because the caller declared the two directions mutual transposes, ``set_reverse``) and runs
+    forward + backward of both directions on two streams; a scalar loss read-back ends the step."""
+    import torch
+    from stargcn_b200 import runtime
+    from stargcn_b200.graph import MultiLinkCSR
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    slots = []
+    for _ in range(2):
+        slot = {}
+        for side, h in host.items():
+            s = sides[side]
+            csr = MultiLinkCSR(h["ep_l"], h["ptr_l"], h["sup_l"], n_nb=s["csr"].n_nb, device=dev)
+            slot[side] = dict(csr=csr, x=torch.empty(h["x"].shape, dtype=torch.float32, device=dev).requires_grad_(True))
+        slot["user"]["csr"].set_reverse(slot["item"]["csr"])
+        slot["item"]["csr"].set_reverse(slot["user"]["csr"])
+        for side in host:
+            slot[side]["csr"].prepare(backward=True)
+        slots.append(slot)
+    torch.cuda.synchronize()
+
+    def make_step(slot):
+        holder = {}
+
+        def one_side(side):
+            s, d = sides[side], slot[side]
+            d["x"].grad = None
+            for p in s["agg"].parameters():
+                p.grad = None
+            d["csr"].rebuild_()
+            out = s["agg"](d["x"], d["csr"])
+            loss = 0.5 * (out * out).mean()
+            loss.backward()
+            holder[side] = loss.detach()
+
+        def fn():
+            with runtime.fork_join(side_streams) as run:
+                for k, side in enumerate(("user", "item")):
+                    run(k, lambda side=side: one_side(side))
+            holder["total"] = holder["user"] + holder["item"]
+        return fn, holder
+
+    def upload(slot):
+        for side, h in host.items():
+            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"])
+            with torch.no_grad():
+                slot[side]["x"].copy_(h["x"], non_blocking=True)
+
+    for slot in slots:
+        upload(slot)
+    torch.cuda.synchronize()
+    graphs = []
+    for slot in slots:
+        fn, holder = make_step(slot)
+        graphs.append((runtime.GraphedStep(fn), holder))
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    for ev in done:
+        ev.record(main)
+    copy_ev, comp_ev = [], []
+
+    def issue_upload(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[k])             # the graph that last read this slot has finished
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(copy_stream)
+            upload(slots[k])
+            c1.record(copy_stream)
+            copy_ev.append((c0, c1))
+            ready[k].record(copy_stream)
+
+    counter = [0]
+
+    def step():
+        i = counter[0]
+        counter[0] += 1
+        k = i % 2
+        main.wait_event(ready[k])
+        issue_upload((i + 1) % 2)                       # prefetch the next step's inputs
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(main)
+        graphs[k][0]()
+        g1.record(main)
+        done[k].record(main)
+        comp_ev.append((g0, g1))
+        return float(graphs[k][1]["total"].item())      # D2H read of the step's result
+
+    steps = max(3, min(args.steps, 50))
+    issue_upload(0)
+    for _ in range(4):
+        step()
+    barrier()
+    del copy_ev[:], comp_ev[:]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    h2d_ms = sum(a.elapsed_time(b) for a, b in copy_ev) / max(len(copy_ev), 1)
+    gpu_ms = sum(a.elapsed_time(b) for a, b in comp_ev) / max(len(comp_ev), 1)
+    return dict(value=total_edges / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, h2d_bytes_per_step=int(h2d),
+                d2h_bytes_per_step=4,
+                call="csr.load_lists_(end_points_l, indptr_l, support_l) from pinned per-level host lists (both directions) + x.copy_() "
+                     "-> one CUDA graph: csr.rebuild_() + MultiLinkGCNAggregator(x, csr) + loss.backward() -> loss.item()",
+                breakdown=dict(h2d_ms=round(h2d_ms, 4), h2d_gbs=round(h2d / (h2d_ms * 1e-3) / 1e9, 2) if h2d_ms else None,
+                               gpu_compute_ms=round(gpu_ms, 4),
+                               note="copy-stream and compute-stream busy time per step (they overlap); the copy is the floor: "
+                                    "PCIe moves the step's lists at the rate shown"),
+                includes="H2D of the 3*R per-level lists + features of both directions from pinned memory (double-buffered: the next "
+                "step's copy overlaps this step's compute), device-side concatenation, plan rebuild in the graph (schedules; transposed "
+                "operands derived from the reverse direction's plan — the caller declares the directions mutual transposes), the two "
+                "directions on two streams, fwd+bwd, scalar loss read-back")
 
 
 def main():

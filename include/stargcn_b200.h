@@ -174,6 +174,18 @@ int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const f
 int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_perm,
                                   const int32_t *t_seg, const float *support, int R, int n_dst, int nnz,
                                   sg_stream_t stream);
+/* The same transposed operands WITHOUT a sort, from the plan of the REVERSE direction when the two plans are each
+ * other's transpose (both directions of a full-neighbourhood bipartite layer; end points ascending inside every
+ * segment): rev_* is the reverse direction's concatenated CSR (R * n_nb segments whose end points are this plan's
+ * destination rows); the weights are this plan's own (found by binary search in its segment).  Bit-identical to
+ * sg_csr_transpose + sg_multilink_transpose_finish on such a pair; *not_found (device) counts reverse edges the
+ * plan does not hold (0 for a true pair).  ws needs sg_multilink_transpose_from_reverse_ws_bytes(n_nb) bytes. */
+size_t sg_multilink_transpose_from_reverse_ws_bytes(int n_nb);
+int sg_multilink_transpose_from_reverse(int32_t *t_indptr /*n_nb+1*/, int32_t *t_src /*nnz*/, float *t_w /*nnz*/,
+                                        int32_t *not_found /*1*/, const int32_t *rev_end_points,
+                                        const int32_t *rev_cat_indptr /*R*n_nb+1*/, const int32_t *end_points,
+                                        const int32_t *cat_indptr /*R*n_dst+1*/, const float *support, int R, int n_dst,
+                                        int n_nb, int nnz, void *ws, sg_stream_t stream);
 int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, const float *t_w,
                          const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
                          int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,
@@ -281,6 +293,14 @@ int sg_remove_edges_count(int32_t *dst_indptr, const int32_t *indptr, const int3
 int sg_remove_edges_fill(int32_t *dst_end_points, float *dst_values, const int32_t *dst_indptr,
                          const int32_t *indptr, const int32_t *end_points, const float *values, int n_rows,
                          int nnz, const void *ws, sg_stream_t stream);
+/* Edge weights of a STATIC relation-major plan over the whole graph when a batch of edges is masked out instead of
+ * removed (replaces the per-iteration CSR rebuild of remove_edges + get_support, graph.py:952-974 /
+ * graph_sampler.cpp:393-420): plan position q (base position split_index[q], row plan_row[q], column plan_col[q])
+ * gets 0 if keep[base position] == 0, else 1/sqrt(d_row d_col) with d = degrees after the removal
+ * (new_*_ptr: the prefix sums sg_remove_edges_count writes for this matrix / for the reverse matrix). */
+int sg_masked_support(float *support /*nnz*/, const int32_t *keep, const int32_t *new_row_ptr, const int32_t *new_col_ptr,
+                      const int32_t *split_index, const int32_t *plan_row, const int32_t *plan_col, int nnz, int symm,
+                      sg_stream_t stream);
 /* counts[b] = |{i : idx[i] == b}| (column degrees after a removal; np.bincount) */
 int sg_bincount(int32_t *counts /*n_bins*/, const int32_t *idx, int n, int n_bins, sg_stream_t stream);
 
@@ -318,6 +338,12 @@ int sg_multi_adam(float *const *params, float *const *grads, float *const *ms, f
  * weight or epilogue — and write one row: out[blocks * 16, 64].  Bytes moved =
  * blocks * 16 * reads_per_group * 256.
  * ---------------------------------------------------------------------------------------- */
+/* Measurement aid: TMA delivery rate to one SM — `blocks` CTAs each stream `iters` ring slots of `boxes`
+ * [32 floats x 128 rows] boxes (16 KB each) of src[rows, K] (ld floats per row) through `stages` slots.
+ * Bytes moved = blocks * |iters| * boxes * 16384; iters < 0: every CTA reads the SAME boxes (hot L2 lines, the
+ * access pattern of a weight tile shared by all CTAs); stages + 100 * (P - 1): P producer warps share a stage's boxes. */
+int sg_tma_probe(const float *src, int rows, int K, int ld, int stages, int boxes, int iters, int blocks,
+                 sg_stream_t stream);
 int sg_row_gather_probe(float *out, const float *table, int n_rows, int reads_per_group, int blocks,
                         unsigned seed, sg_stream_t stream);
 

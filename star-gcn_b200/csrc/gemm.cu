@@ -46,6 +46,8 @@ struct GemmArgs {
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
   const float *bias; // optional [N], added before the activation
+  int split_exp;      // experiment bits (SG_DEV_GEMM_SPLIT_EXP)
+  int a_block_rows;   // experiment: > 0 = K-major A stored k-block-major, this many rows per block
   int relaxed_arrive; // hand the TMEM buffer back with a relaxed arrival (default; see mbar_arrive_leader_relaxed)
 };
 
@@ -286,8 +288,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               tma_load_2d_pair(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
             }
           } else {
-            tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
-            tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
+            const int ac0 = g.a_block_rows ? 0 : kb * kBK, ac1 = g.a_block_rows ? kb * g.a_block_rows + m0 : m0;
+            tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], ac0, ac1);
+            tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], ac0, ac1);
             tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
             tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
           }
@@ -318,8 +321,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
                          sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
-            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+          for (int pass = 0; pass < 3; ++pass) {  // hi.hi, hi.lo, then lo.hi (the order the split kernel needs)
+            const uint32_t sa = pass == 2 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               uint64_t da, db;
@@ -409,22 +412,239 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same CTA-pair kernel with FOUR TMA producer warps.
+//
+// What bounded the kernel above is not the memory system but the single issuing thread: a thread that issues
+// [32 floats x 128 rows] boxes delivers 35 / 48 / 57 GB/s per SM at 1 / 2 / 4 boxes per barrier phase no matter
+// how many stages are in flight or whether the source sits in L2 or DRAM (t = 0.24 us + 0.23 us per box), while
+// two / four issuing WARPS reach 87 / 132 GB/s per SM on the same ring (tools/gemm_bench.py, sg_tma_probe;
+// profiles/r02_summary.md).  A 64 KB stage (A_hi, A_lo, B_hi, B_lo) took 1.15 us to issue against 0.84 us of
+// tensor work.  Here each of the four operand tiles of a stage has its own producer warp (MN-major: each warp
+// issues one of the four 32-column atoms of all four tiles), and the warp-group register budgets of the split
+// kernel below pay for the extra warps: WG0 = 4 producers (40), WG1-2 = 8 epilogue warps (208), WG3 = MMA warp,
+// TMEM allocator, 2 idle (56).
+// ---------------------------------------------------------------------------------------------
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int kPair4Threads = 512;
+
+template <int STAGES, bool MN_MAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPair4Threads, 1)
+    tf32x3_gemm_pair4_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                             const GemmArgs g) {
+  constexpr int BN = 256;
+  constexpr int A_BYTES = kBM * kBK * 4;
+  constexpr int B_BYTES = 128 * kBK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int STG_FLOATS = 32 * 33;
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
+                                  ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+  __shared__ uint64_t full_bar[STAGES];    // leader only: TMA bytes of both CTAs (one arrival: the leader's producer 0)
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];   // leader only
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;
+  const int n_tiles = tiles_mn * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 12 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 13) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    // ---- four TMA producer warps (both CTAs): warp p owns operand tile p (K-major) / atom p of every tile (MN-major) ----
+    reg_dec<40>();
+    if (lane == 0) {
+      const int p = warp;
+      int v = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const int nb0 = n0 + (int)rank * (n_eff >> 1);
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader && p == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // the ONE arrival; bytes of both CTAs
+          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
+          if constexpr (MN_MAJOR) {
+            tma_load_2d_pair(sa_hi + p * (kBK * 128), &map_a_hi, &full_bar[s], m0 + p * 32, kb * kBK);
+            tma_load_2d_pair(sa_lo + p * (kBK * 128), &map_a_lo, &full_bar[s], m0 + p * 32, kb * kBK);
+            tma_load_2d_pair(sb_hi + p * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + p * 32, kb * kBK);
+            tma_load_2d_pair(sb_lo + p * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + p * 32, kb * kBK);
+          } else {
+            if (p == 0) tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
+            else if (p == 1) tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
+            else if (p == 2) tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
+            else tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    reg_dec<56>();
+    if (warp == 12 && leader && lane == 0) {
+      int v = 0, chain = 0;
+      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+        const int n0 = (rem % tiles_n) * BN;
+        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+        const int n_kb = kb_end - kb_begin;
+        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
+        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        for (int i = 0; i < n_kb; ++i, ++v) {
+          const int s = v % STAGES;
+          const uint32_t ph = (v / STAGES) & 1;
+          const int vin = i % g.chain_kb;
+          const int buf = chain & 1;
+          if (vin == 0) {
+            mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
+                         sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {  // hi.hi, hi.lo, lo.hi
+            const uint32_t sa = pass == 2 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              uint64_t da, db;
+              if constexpr (MN_MAJOR) {
+                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
+                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
+              } else {
+                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+              }
+              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != 0) || (k != 0));
+            }
+          }
+          umma_commit_pair(&empty_bar[s]);
+          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
+            umma_commit_pair(&tmem_full_bar[buf]);
+            ++chain;
+          }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps 4..11 ----
+    reg_inc<208>();
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const int cbase = h * (BN / 2);
+    float *stg = stg_all + (warp - 4) * STG_FLOATS;
+    int chain = 0;
+    for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
+      const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
+      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
+      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
+      const bool active = n0 + cbase < g.N && m0 < g.M;  // warp-uniform
+      float racc[BN / 2];
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
+      for (int c = 0; c < n_chains; ++c, ++chain) {
+        const int buf = chain & 1;
+        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+        tc_fence_after();
+        if (active) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (g.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty_bar[buf]);
+          else mbar_arrive_leader(&tmem_empty_bar[buf]);
+        }
+      }
+      if (active) {
+        float *dbase = g.D + (long long)z * g.split_stride;
+        const int row0 = m0 + q * 32;
+#pragma unroll
+        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
+          const int col = n0 + cbase + ch * 32 + lane;
+          if (n0 + cbase + ch * 32 >= g.N) break;
+          float bias = 0.f;
+          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
+          __syncwarp();
+          const int rows = min(32, g.M - row0);
+          for (int rr = 0; rr < rows; ++rr) {
+            float x = stg[rr * 33 + lane] + bias;
+            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
+            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 13) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CTA-pair kernel with the hi/lo operand split done INSIDE the kernel.
 //
-// The pre-split kernels above stream 8 bytes per operand element (hi + lo) through the L2->SM fabric and
-// need a producer pass that writes both halves to HBM.  Here an operand arrives as plain fp32: TMA lands
-// the raw tile in the "hi" slot of the stage, four splitter warps rewrite it in place as the TF32-exact
-// high part and store the remainder to the "lo" slot (the split is element-wise, so the swizzled layout
-// TMA produced is preserved), `fence.proxy.async` makes the generic-proxy stores visible to the tensor
-// core's async-proxy reads, and a second barrier (on the leader CTA, 4 warps x 2 CTAs arrivals) tells the
-// MMA warp that the stage is ready in BOTH CTAs.  A is always split in the kernel; B either arrives
-// pre-split (small weight matrices, split once per call) or raw (SPLIT_B: the weight gradient, whose B
-// operand is the aggregated feature matrix).
+// The pre-split kernel above streams 8 bytes per operand element (hi + lo) through the L2->SM fabric and needs a
+// producer pass that writes both halves to HBM.  Here an operand arrives as plain fp32.  Two facts make that cheap:
+//   * the tensor core TRUNCATES fp32 inputs to TF32 (measured: feeding the raw tile as the "hi" operand gives
+//     bit-identical results to feeding x & 0xffffe000, tools/gemm_bench.py) — so the raw tile TMA delivers IS the
+//     hi operand and only the remainder lo = x - trunc(x) has to be produced;
+//   * of the three products  hi.hi + hi.lo + lo.hi  only those with a "lo" factor wait for that remainder.
+// Four splitter warps compute lo from the raw tile (element-wise, so the swizzled layout TMA produced is preserved),
+// `fence.proxy.async` makes their generic-proxy stores visible to the tensor core's async-proxy reads, and a second
+// barrier on the leader CTA (4 warps x 2 CTAs arrivals) releases the lo products; the MMA warp issues the hi
+// products as soon as the TMA bytes of BOTH CTAs have landed (same critical path as the pre-split kernel, 25 - 50 %
+// fewer bytes).  All TMA loads complete on the LEADER's full barrier (cta_group::2); the leader's splitter relays
+// that to the peer CTA's splitter warps through `go_bar`.  A is always raw; B is pre-split (small weight matrices,
+// split once per call) or raw (SPLIT_B: the weight gradient, whose B operand is the aggregated feature matrix).
 //
 // 512 threads = 4 warpgroups with their own register budgets (setmaxnreg): WG0 = TMA warp, MMA warp, TMEM
 // allocator (40 registers), WG1-2 = 8 epilogue warps holding the 128 fp32 accumulators of the chained TMEM
 // drain (208), WG3 = 4 splitter warps (56); 128 x (40 + 208 + 208 + 56) = the whole register file.
-// Each CTA's TMA loads complete on its OWN full barrier (the splitter warps of that CTA wait there).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSplitThreads = 512;
 constexpr int kSplitterWarps = 4;
@@ -441,26 +661,31 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-
-// hi/lo split of one 16 KB operand tile by the 128 splitter threads (conflict-free 16-byte accesses)
-__device__ __forceinline__ void split_tile_16k(uint8_t *hi_slot, uint8_t *lo_slot, int st) {
+// lo = x - trunc_tf32(x) of one 16 KB operand tile by the 128 splitter threads (conflict-free 16-byte accesses);
+// the raw tile stays in place as the hi operand
+__device__ __forceinline__ void split_tile_16k(const uint8_t *raw_slot, uint8_t *lo_slot, int st) {
   constexpr int kVecs = 16384 / 16 / (kSplitterWarps * 32);  // 8 float4 per thread
   float4 v[kVecs];
 #pragma unroll
-  for (int i = 0; i < kVecs; ++i) v[i] = reinterpret_cast<const float4 *>(hi_slot)[i * (kSplitterWarps * 32) + st];
+  for (int i = 0; i < kVecs; ++i) v[i] = reinterpret_cast<const float4 *>(raw_slot)[i * (kSplitterWarps * 32) + st];
 #pragma unroll
   for (int i = 0; i < kVecs; ++i) {
-    float4 h;
-    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
-    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
-    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
-    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
-    reinterpret_cast<float4 *>(hi_slot)[i * (kSplitterWarps * 32) + st] = h;
-    reinterpret_cast<float4 *>(lo_slot)[i * (kSplitterWarps * 32) + st] =
-        make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+    float4 l;
+    l.x = v[i].x - __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
+    l.y = v[i].y - __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
+    l.z = v[i].z - __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
+    l.w = v[i].w - __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+    reinterpret_cast<float4 *>(lo_slot)[i * (kSplitterWarps * 32) + st] = l;
   }
+}
+
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t *bar) {  // arrive on the non-leader CTA's copy of `bar`
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int STAGES, bool MN_MAJOR, bool SPLIT_B>
@@ -479,9 +704,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
-  __shared__ uint64_t full_bar[STAGES];    // this CTA's TMA bytes
+  __shared__ uint64_t full_bar[STAGES];    // leader only: TMA bytes of BOTH CTAs
+  __shared__ uint64_t go_bar[STAGES];      // peer only: the leader saw full_bar complete (relayed by its splitter)
   __shared__ uint64_t empty_bar[STAGES];   // MMAs that read the stage have completed (multicast commit)
-  __shared__ uint64_t split_bar[STAGES];   // leader only: stage split in both CTAs (2 x kSplitterWarps arrivals)
+  __shared__ uint64_t split_bar[STAGES];   // leader only: lo tiles written in both CTAs (2 x kSplitterWarps arrivals)
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];   // leader only
   __shared__ uint32_t tmem_base_smem;
@@ -500,7 +726,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 2 * kSplitterWarps);
+      mbar_init(&full_bar[s], 1); mbar_init(&go_bar[s], 1); mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 2 * kSplitterWarps);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
     fence_barrier_init();
@@ -529,24 +756,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
           const int s = v % STAGES;
           const uint32_t ph = (v / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], TX_BYTES);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * TX_BYTES);  // bytes of BOTH CTAs land on the leader's barrier
           uint8_t *sa_hi = smem + s * STAGE_BYTES, *sb_hi = sa_hi + 2 * A_BYTES, *sb_lo = sb_hi + B_BYTES;
           if constexpr (MN_MAJOR) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-              tma_load_2d(sa_hi + a * (kBK * 128), &map_a, &full_bar[s], m0 + a * 32, kb * kBK);
-              tma_load_2d(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + a * 32, kb * kBK);
-              if constexpr (!SPLIT_B) tma_load_2d(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
+              tma_load_2d_pair(sa_hi + a * (kBK * 128), &map_a, &full_bar[s], m0 + a * 32, kb * kBK);
+              tma_load_2d_pair(sb_hi + a * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + a * 32, kb * kBK);
+              if constexpr (!SPLIT_B) tma_load_2d_pair(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
             }
           } else {
-            tma_load_2d(sa_hi, &map_a, &full_bar[s], kb * kBK, m0);
-            tma_load_2d(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
-            if constexpr (!SPLIT_B) tma_load_2d(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
+            tma_load_2d_pair(sa_hi, &map_a, &full_bar[s], kb * kBK, m0);
+            tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
+            if constexpr (!SPLIT_B) tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
           }
         }
       }
     } else if (warp == 1 && leader && lane == 0) {
-      // ---- MMA issuer (leader CTA): waits for the split stage of BOTH CTAs ----
+      // ---- MMA issuer (leader CTA): hi products when the TMA bytes have landed, lo products after the split ----
       int v = 0, chain = 0;
       for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
         const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
@@ -561,16 +788,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
           const int vin = i % g.chain_kb;
           const int buf = chain & 1;
           if (vin == 0) {
-            mbar_wait_cluster(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            if (g.split_exp & 8) mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            else mbar_wait_cluster(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
             tc_fence_after();
           }
-          mbar_wait_cluster(&split_bar[s], ph);
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
                          sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // lo.hi, hi.lo, then hi.hi
-            const uint32_t sa = pass == 0 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
+          for (int pass = 0; pass < 3; ++pass) {  // hi.hi, hi.lo, lo.hi
+            // the raw tiles are the hi operands; a pre-split B_lo arrives by TMA, everything else "lo" by the splitters
+            if ((pass == 1 && SPLIT_B) || (pass == 2 && !SPLIT_B)) {
+              if (g.split_exp & 8) mbar_wait(&split_bar[s], ph);
+              else mbar_wait_cluster(&split_bar[s], ph);
+              tc_fence_after();
+            }
+            const uint32_t sa = pass == 2 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               uint64_t da, db;
@@ -593,7 +827,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
       }
     }
   } else if (warp >= 12) {
-    // ---- splitter warps (both CTAs) ----
+    // ---- splitter warps (both CTAs): lo = x - trunc(x) of the raw tiles ----
     reg_dec<56>();
     const int st = threadIdx.x - 12 * 32;
     int v = 0;
@@ -603,13 +837,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
       for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
         const int s = v % STAGES;
         const uint32_t ph = (v / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+        if (leader) {
+          mbar_wait(&full_bar[s], ph);
+          if (warp == 12 && lane == 0) mbar_arrive_peer(&go_bar[s]);   // relay: the peer's bytes have landed as well
+        } else {
+          mbar_wait_cluster(&go_bar[s], ph);
+        }
         uint8_t *sa_hi = smem + s * STAGE_BYTES;
-        split_tile_16k(sa_hi, sa_hi + A_BYTES, st);
-        if constexpr (SPLIT_B) split_tile_16k(sa_hi + 2 * A_BYTES, sa_hi + 2 * A_BYTES + B_BYTES, st);
-        fence_proxy_async_smem();
+        if (!(g.split_exp & 4)) {
+          split_tile_16k(sa_hi, sa_hi + A_BYTES, st);
+          if constexpr (SPLIT_B) split_tile_16k(sa_hi + 2 * A_BYTES, sa_hi + 2 * A_BYTES + B_BYTES, st);
+        }
+        if (!(g.split_exp & 2)) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&split_bar[s]);
+        if (lane == 0) {
+          if (g.split_exp & 1) mbar_arrive_leader_relaxed(&split_bar[s]);
+          else mbar_arrive_leader(&split_bar[s]);
+        }
       }
     }
   } else {
@@ -678,6 +922,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement aid: what can TMA deliver to one SM?  Every CTA streams [32 floats x 128 rows] boxes (16 KB, the A
+// tile of the GEMMs) of a row-major matrix through a ring of `stages` slots of `boxes` boxes each; a consumer
+// thread frees a slot as soon as it has landed.  No MMA, no epilogue: GB/s per SM as a function of the bytes in
+// flight separates a latency bound (rate grows with the ring) from a throughput bound (rate flat).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1) tma_probe_kernel(const __grid_constant__ CUtensorMap map, int rows, int kb_total,
+                                                           int stages, int boxes, int iters, int same_boxes, int producers) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[16];
+  __shared__ uint64_t empty_bar[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], producers); mbar_init(&empty_bar[s], 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int tiles_m = rows / kBM;
+  if (warp < producers && lane == 0) {       // producer warp p issues boxes p, p + producers, ... of every stage
+    const int mine = (boxes - warp + producers - 1) / producers;
+    for (int v = 0; v < iters; ++v) {
+      const int s = v % stages;
+      const uint32_t ph = (v / stages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_expect_tx(&full_bar[s], mine * kBM * kBK * 4);
+      for (int b = warp; b < boxes; b += producers) {
+        // a different box every time; same_boxes: every CTA walks the SAME boxes (hot L2 lines)
+        const long long t = ((long long)(same_boxes ? 0 : blockIdx.x) * iters + v) * boxes + b;
+        const int m0 = (int)(t % tiles_m) * kBM, kb = (int)((t / tiles_m) % kb_total);
+        tma_load_2d(smem + (s * boxes + b) * (kBM * kBK * 4), &map, &full_bar[s], kb * kBK, m0);
+      }
+    }
+  } else if (warp == 4 && lane == 0) {
+    for (int v = 0; v < iters; ++v) {
+      const int s = v % stages;
+      const uint32_t ph = (v / stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      mbar_arrive(&empty_bar[s]);
+    }
   }
 }
 
@@ -829,6 +1116,21 @@ static int launch_gemm_pair(const CUtensorMap (&maps)[4], GemmArgs g, int splits
   return SG_OK;
 }
 
+template <int STAGES, bool MN>
+static int launch_gemm_pair4(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
+  SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_pair4_kernel<STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g.tiles_m = ceil_div(g.M, 256);
+  g.tiles_n = ceil_div(g.N, 256);
+  g.splits = splits;
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = (int)(n_tiles < max_pairs ? n_tiles : max_pairs);
+  tf32x3_gemm_pair4_kernel<STAGES, MN><<<2 * pairs, kPair4Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  SG_LAUNCHED("tf32x3_gemm_pair4_kernel");
+  return SG_OK;
+}
+
 template <int STAGES, bool MN, bool SPLIT_B>
 static int launch_gemm_split(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
   constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
@@ -879,6 +1181,8 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
   g.M = M; g.N = N; g.epi = epilogue; g.slope = slope; g.bias = bias;
   g.chain_kb = dev_option(SG_DEV_GEMM_CHAIN) > 0 ? dev_option(SG_DEV_GEMM_CHAIN) : kChainKBlocks;
   g.relaxed_arrive = dev_option(SG_DEV_GEMM_ARRIVE) == 0;
+  g.a_block_rows = (!mn_major && A_lo) ? dev_option(SG_DEV_GEMM_A_BLOCK_ROWS) : 0;
+  g.split_exp = dev_option(SG_DEV_GEMM_SPLIT_EXP);
   g.kb_total = ceil_div(K, kBK);
   g.kb_per_split = ceil_div(g.kb_total, splits);
   splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split
@@ -893,21 +1197,49 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
     if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[3], B_lo ? B_lo : B_hi, K, N, ldb)) != SG_OK) return rc;
     if (!A_lo) rc = B_lo ? launch_gemm_split<3, true, false>(maps, g, splits, st) : launch_gemm_split<3, true, true>(maps, g, splits, st);
-    else rc = launch_gemm_pair<3, true>(maps, g, splits, st);
+    else rc = dev_option(SG_DEV_GEMM_PRODUCERS) == 1 ? launch_gemm_pair<3, true>(maps, g, splits, st)
+                                                     : launch_gemm_pair4<3, true>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   } else {
-    if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
-    if ((rc = make_map_kmajor(&maps[1], A_lo ? A_lo : A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+    if (g.a_block_rows > 0) {   // [kb][rows][32]: a matrix of 32 columns and kb_total * rows rows
+      if ((rc = make_map_kmajor(&maps[0], A_hi, g.kb_total * g.a_block_rows, kBK, kBK, kBM)) != SG_OK) return rc;
+      if ((rc = make_map_kmajor(&maps[1], A_lo, g.kb_total * g.a_block_rows, kBK, kBK, kBM)) != SG_OK) return rc;
+    } else {
+      if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+      if ((rc = make_map_kmajor(&maps[1], A_lo ? A_lo : A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+    }
     if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, 128)) != SG_OK) return rc;   // a CTA of a pair loads half of the B tile
     if ((rc = make_map_kmajor(&maps[3], B_lo ? B_lo : B_hi, N, K, ldb, 128)) != SG_OK) return rc;
     if (!A_lo) rc = B_lo ? launch_gemm_split<3, false, false>(maps, g, splits, st) : launch_gemm_split<3, false, true>(maps, g, splits, st);
-    else rc = launch_gemm_pair<3, false>(maps, g, splits, st);
+    else rc = dev_option(SG_DEV_GEMM_PRODUCERS) == 1 ? launch_gemm_pair<3, false>(maps, g, splits, st)
+                                                     : launch_gemm_pair4<3, false>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   }
   if (splits > 1) {
     splitk_reduce_kernel<<<grid_ew((long long)M * N), 256, 0, st>>>(D, ldd, split_ws, M, N, splits);
     SG_LAUNCHED("splitk_reduce_kernel");
   }
+  return SG_OK;
+}
+
+/* Measurement aid (tools/gemm_bench.py): TMA delivery rate per SM, see tma_probe_kernel. */
+int sg_tma_probe(const float *src, int rows, int K, int ld, int stages, int boxes, int iters, int blocks, sg_stream_t stream) {
+  // encoding kept in one int to leave the signature alone: stages = real stages + 100 * (producer warps - 1)
+  const int producers = stages / 100 + 1;
+  stages %= 100;
+  SG_REQUIRE(producers >= 1 && producers <= 4 && producers <= boxes, "sg_tma_probe: 1..4 producer warps, at most one per box");
+  const int same_boxes = iters < 0;       // negative iters: all CTAs read the same sequence of boxes (hot lines)
+  if (iters < 0) iters = -iters;
+  SG_REQUIRE(src && rows >= kBM && K >= kBK && (ld & 3) == 0 && stages >= 1 && stages <= 16 && boxes >= 1 && iters >= 1 && blocks >= 1,
+             "sg_tma_probe: bad arguments");
+  const int smem = stages * boxes * kBM * kBK * 4 + 1024;
+  SG_REQUIRE(smem <= 227 * 1024, "sg_tma_probe: ring of %d bytes does not fit shared memory", smem);
+  CUtensorMap map;
+  int rc = make_map_kmajor(&map, src, rows, K, ld, kBM);
+  if (rc != SG_OK) return rc;
+  SG_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tma_probe_kernel<<<blocks, 160, smem, (cudaStream_t)stream>>>(map, rows, K / kBK, stages, boxes, iters, same_boxes, producers);
+  SG_LAUNCHED("tma_probe_kernel");
   return SG_OK;
 }
 

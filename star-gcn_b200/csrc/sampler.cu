@@ -103,6 +103,40 @@ __global__ void __launch_bounds__(256) support_kernel(float *__restrict__ suppor
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Static full-graph plans (stargcn_b200.static_step): instead of rebuilding both CSR directions without the batch
+// edges every iteration (remove_edges, graph.py:952-974) the WHOLE training graph stays in one relation-major plan
+// and only its edge weights change: a removed edge gets weight 0 (fma(0, x, acc) == acc: bit-neutral), a kept
+// edge the normalisation 1/sqrt(d_row d_col) with the degrees of the graph WITHOUT the removed edges — evaluated
+// exactly as get_support does (graph_sampler.cpp:393-420).
+//   keep[p]          1 / 0 per position of the base CSR (sg_remove_edges_count's marking pass)
+//   new_row_ptr      prefix sums of the kept edges per row (same call) -> degrees after removal
+//   new_col_ptr      the same of the REVERSE direction's matrix (its rows are this matrix's columns)
+//   split_index[q]   base position of plan position q,  plan_row[q] its row,  plan_col[q] its column
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) masked_support_kernel(float *__restrict__ support, const int32_t *__restrict__ keep,
+                                                             const int32_t *__restrict__ new_row_ptr,
+                                                             const int32_t *__restrict__ new_col_ptr,
+                                                             const int32_t *__restrict__ split_index,
+                                                             const int32_t *__restrict__ plan_row,
+                                                             const int32_t *__restrict__ plan_col, int nnz, int symm) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    if (__ldg(keep + __ldg(split_index + q)) != 0) {
+      const int i = __ldg(plan_row + q);
+      const int r_deg = __ldg(new_row_ptr + i + 1) - __ldg(new_row_ptr + i);
+      if (symm) {
+        const int j = __ldg(plan_col + q);
+        const int c_deg = __ldg(new_col_ptr + j + 1) - __ldg(new_col_ptr + j);
+        if (r_deg != 0 && c_deg != 0) s = __fsqrt_rn(__fdiv_rn(__fdiv_rn(1.0f, (float)r_deg), (float)c_deg));
+      } else if (r_deg != 0) {
+        s = __fdiv_rn(1.0f, (float)r_deg);
+      }
+    }
+    support[q] = s;
+  }
+}
+
 __device__ __forceinline__ int level_of(float v, const float *__restrict__ possible, int R) {
   int lvl = -1;
   for (int r = 0; r < R; ++r)
@@ -364,6 +398,19 @@ int sg_remove_edges_fill(int32_t *dst_end_points, float *dst_values, const int32
   compact_rows_kernel<<<grid_w(n_rows), 256, 0, (cudaStream_t)stream>>>(dst_end_points, dst_values, dst_indptr,
                                                                         static_cast<const int32_t *>(ws), end_points, values, indptr, n_rows);
   SG_LAUNCHED("compact_rows_kernel");
+  return SG_OK;
+}
+
+int sg_masked_support(float *support, const int32_t *keep, const int32_t *new_row_ptr, const int32_t *new_col_ptr,
+                      const int32_t *split_index, const int32_t *plan_row, const int32_t *plan_col, int nnz, int symm,
+                      sg_stream_t stream) {
+  SG_REQUIRE(nnz >= 0, "sg_masked_support: negative size");
+  if (nnz == 0) return SG_OK;
+  SG_REQUIRE(support && keep && new_row_ptr && split_index && plan_row && (!symm || (new_col_ptr && plan_col)),
+             "sg_masked_support: null pointer");
+  masked_support_kernel<<<grid_w(ceil_div(nnz, 32)), 256, 0, (cudaStream_t)stream>>>(support, keep, new_row_ptr, new_col_ptr,
+                                                                                    split_index, plan_row, plan_col, nnz, symm);
+  SG_LAUNCHED("masked_support_kernel");
   return SG_OK;
 }
 

@@ -101,6 +101,30 @@ class MultiLinkCSR:
             if flags[1]:
                 raise ValueError("end point index out of range of the neighbour feature matrix")
         self._init_device(ep_cat, sup_cat, cat_indptr, chunk, use_schedule)
+        self._ptr2, self._offs_dev, self._offs = ptr2, offs_dev, offs
+
+    def load_lists_(self, end_points_l, indptr_l, support_l):
+        """Refresh the plan IN PLACE from new per-level lists with the SAME per-level edge counts (same-shaped plan
+        of the next iteration): every level is copied straight into its slice of the existing device arrays
+        (asynchronously from pinned memory) and the concatenated indptr is re-assembled on the device.  The derived
+        structures are stale afterwards — call :meth:`rebuild_` (CUDA-graph capturable) before the next use."""
+        if getattr(self, "_ptr2", None) is None:
+            raise ValueError("load_lists_ needs a plan that was built from per-level lists")
+        R, n_dst, offs = self.R, self.n_dst, self._offs
+        if not (len(end_points_l) == len(indptr_l) == len(support_l) == R):
+            raise ValueError("the refreshed lists must have the same number of levels")
+        for r in range(R):
+            n = self.nnz_l[r]
+            e, s_, p = (_as_tensor(end_points_l[r], torch.int32), _as_tensor(support_l[r], torch.float32),
+                        _as_tensor(indptr_l[r], torch.int32))
+            if p.shape[0] != n_dst + 1 or e.shape[0] < n or s_.shape[0] < n:
+                raise ValueError(f"level {r}: shape differs from the plan being refreshed")
+            if n:
+                self.end_points[offs[r]:offs[r + 1]].copy_(e[:n], non_blocking=True)
+                self.support[offs[r]:offs[r + 1]].copy_(s_[:n], non_blocking=True)
+            self._ptr2[r].copy_(p, non_blocking=True)
+        self.cat_indptr[:R * n_dst].view(R, n_dst).copy_(self._ptr2[:, :n_dst] + self._offs_dev[:, None])
+        return self
 
     @classmethod
     def from_device(cls, end_points, support, cat_indptr, R, n_dst, n_nb, chunk=DEFAULT_CHUNK, use_schedule=True):
@@ -123,37 +147,111 @@ class MultiLinkCSR:
         self.use_schedule = bool(use_schedule)
         self._sched = None
         self._t = None
+        self._t_ws = None
         self._t_sched = None
+        self._reverse = None
+        self._not_found = None
+        self._ptr2 = None
         self.h2d_bytes = 4 * (2 * self.nnz + self.n_seg + 1)
+
+    def set_reverse(self, other):
+        """Declare ``other`` to be the plan of the REVERSE direction over the same edge set with the same edge
+        (both directions of a full-neighbourhood bipartite layer; end points ascending inside every segment, as
+        scipy's CSR and the reference's split deliver them).  The transposed operands of each plan are then read off
+        the other plan's CSR by two small kernels instead of a radix sort (sg_multilink_transpose_from_reverse;
+        bit-identical result on such a pair).  ``reverse_mismatches()`` tells afterwards whether the declaration held."""
+        if other is not None and not (other.R == self.R and other.nnz == self.nnz and other.n_dst == self.n_nb
+                                      and other.n_nb == self.n_dst):
+            raise ValueError("the reverse plan must have the transposed shape and the same number of edges")
+        self._reverse = other
+        self._t = None
+        self._t_sched = None
+        return self
+
+    def to_lists(self):
+        """The reference's per-level ``(end_points_l, indptr_l, support_l)`` lists as numpy arrays (inspection /
+        tests: a device -> host copy)."""
+        ptr = self.cat_indptr.cpu().numpy().astype(np.int64)
+        ep, sup = self.end_points.cpu().numpy(), self.support.cpu().numpy()
+        ep_l, ptr_l, sup_l = [], [], []
+        for r in range(self.R):
+            seg = ptr[r * self.n_dst:(r + 1) * self.n_dst + 1]
+            ep_l.append(ep[seg[0]:seg[-1]].copy())
+            sup_l.append(sup[seg[0]:seg[-1]].copy())
+            ptr_l.append((seg - seg[0]).astype(np.int32))
+        return ep_l, ptr_l, sup_l
 
     def schedule(self):
         if self.use_schedule and self._sched is None:
             self._sched = Schedule(self.cat_indptr, self.nnz, self.chunk)
         return self._sched
 
-    def transposed(self):
-        """(t_indptr [n_nb+1], t_src [nnz] = i*R + r, t_w [nnz]) built once per plan."""
-        if self._t is None:
-            lib = _lib.load()
-            dev = self.device
-            t_indptr = torch.empty(self.n_nb + 1, dtype=torch.int32, device=dev)
-            n = max(self.nnz, 1)
-            t_perm = torch.empty(n, dtype=torch.int32, device=dev)
-            t_seg = torch.empty(n, dtype=torch.int32, device=dev)
+    def reverse_mismatches(self):
+        """Number of reverse-plan edges this plan does not hold, as seen by the last sort-free transposed build
+        (0 for a true pair of transposes).  Synchronises."""
+        return 0 if self._not_found is None else int(self._not_found.item())
+
+    def _build_transposed(self, out=None):
+        """(t_indptr [n_nb+1], t_src [nnz] = i*R + r, t_w [nnz]); ``out`` = existing buffers to refill in place."""
+        lib = _lib.load()
+        dev = self.device
+        n = max(self.nnz, 1)
+        if out is None:
+            out = (torch.empty(self.n_nb + 1, dtype=torch.int32, device=dev),
+                   torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev))
+        t_indptr, t_src, t_w = out
+        if self._reverse is not None:
+            rev = self._reverse
+            if self._t_ws is None:
+                self._t_ws = (_bytes(lib.sg_multilink_transpose_from_reverse_ws_bytes(self.n_nb), dev),)
+            if self._not_found is None:
+                self._not_found = torch.zeros(1, dtype=torch.int32, device=dev)
+            check(lib.sg_multilink_transpose_from_reverse(_p(t_indptr), _p(t_src), _p(t_w), _p(self._not_found),
+                                                          _p(rev.end_points), _p(rev.cat_indptr), _p(self.end_points),
+                                                          _p(self.cat_indptr), _p(self.support), self.R, self.n_dst,
+                                                          self.n_nb, self.nnz, _p(self._t_ws[0]), _stream()),
+                  "sg_multilink_transpose_from_reverse")
+            return out
+        if self._t_ws is None:
             ws_bytes = lib.sg_csr_transpose_ws_bytes(self.n_seg, self.n_nb, self.nnz)
             if ws_bytes == 0:
                 check(2, "sg_csr_transpose_ws_bytes")
-            ws = _bytes(ws_bytes, dev)
-            check(lib.sg_csr_transpose(_p(t_indptr), _p(t_perm), _p(t_seg), _p(self.end_points), _p(self.cat_indptr),
-                                       self.n_seg, self.n_nb, self.nnz, _p(ws), ws_bytes, _stream()),
-                  "sg_csr_transpose")
-            t_src = torch.empty(n, dtype=torch.int32, device=dev)
-            t_w = torch.empty(n, dtype=torch.float32, device=dev)
-            check(lib.sg_multilink_transpose_finish(_p(t_src), _p(t_w), _p(t_perm), _p(t_seg), _p(self.support),
-                                                    self.R, self.n_dst, self.nnz, _stream()),
-                  "sg_multilink_transpose_finish")
-            self._t = (t_indptr, t_src, t_w)
+            self._t_ws = (_bytes(ws_bytes, dev), ws_bytes, torch.empty(n, dtype=torch.int32, device=dev),
+                          torch.empty(n, dtype=torch.int32, device=dev))
+        ws, ws_bytes, t_perm, t_seg = self._t_ws
+        check(lib.sg_csr_transpose(_p(t_indptr), _p(t_perm), _p(t_seg), _p(self.end_points), _p(self.cat_indptr),
+                                   self.n_seg, self.n_nb, self.nnz, _p(ws), ws_bytes, _stream()), "sg_csr_transpose")
+        check(lib.sg_multilink_transpose_finish(_p(t_src), _p(t_w), _p(t_perm), _p(t_seg), _p(self.support),
+                                                self.R, self.n_dst, self.nnz, _stream()), "sg_multilink_transpose_finish")
+        return out
+
+    def transposed(self):
+        """(t_indptr [n_nb+1], t_src [nnz] = i*R + r, t_w [nnz]) built once per plan."""
+        if self._t is None:
+            self._t = self._build_transposed()
+            if self.nnz > (1 << 20):
+                self._t_ws = None if self._reverse is None else self._t_ws   # the sort scratch (~100 B/edge) is not kept
         return self._t
+
+    def refresh_weights_(self):
+        """The edge weights (``support``) were rewritten in place, the pattern did not change: re-derive only what
+        depends on the weights — the transposed weight array.  CUDA-graph capturable."""
+        if self._t is not None:
+            self._build_transposed(self._t)
+        return self
+
+    def rebuild_(self, backward=True):
+        """Recompute every derived structure (schedules, transposed operands) INTO THE EXISTING BUFFERS after the
+        CSR arrays were refreshed in place (load_lists_, or a device producer writing into them).  Pure kernel
+        launches on the current stream with pre-allocated scratch: capturable in a CUDA graph together with the
+        forward / backward that follows.  Call prepare() once before capturing."""
+        if self._sched is not None:
+            self._sched.rebuild_()
+        if backward and self._t is not None:
+            self._build_transposed(self._t)
+            if self._t_sched is not None:
+                self._t_sched.rebuild_()
+        return self
 
     def t_schedule(self):
         if self.use_schedule and self._t_sched is None:

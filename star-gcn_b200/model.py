@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import decoder
+from . import decoder, devgraph
 from .hetergraph import merge_node_ids_dict
 from .layers import HeterGCNLayer, InnerProductLayer, LayerDictionary, StackedHeterGCNLayers
 from .layers.common import Dense
@@ -29,6 +29,8 @@ class EmbedTable(nn.Module):
 
 
 def _ids(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.int32)
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32)).to(device)
 
 
@@ -77,6 +79,9 @@ class StarGCN(nn.Module):
             raise NotImplementedError("need rating pairs, recon nodes, or both")
         dev = self.device
         gt = self.get_embed(recon_node_ids_dict, use_mask=False) if recon_node_ids_dict is not None else {}
+        # a DeviceHeterGraph keeps the whole plan construction on the device (devgraph.gen_plan): no index array
+        # crosses PCIe in either direction; a host graph object goes through the numpy mirror of the reference
+        on_device = isinstance(graph, devgraph.DeviceHeterGraph)
 
         # ---- plans, last block first: what a block must output = rating nodes + recon nodes + next block's inputs ----
         plans, lookups, needed = [None] * self._n_blocks, [None] * self._n_blocks, {}
@@ -90,10 +95,15 @@ class StarGCN(nn.Module):
                 names.append("recon")
             requests.append(needed)
             names.append("next")
-            selected, idx = merge_node_ids_dict(requests)
-            lookups[b] = dict(zip(names, idx))
-            needed, plans[b] = self.encoders[b].gen_plan(graph=graph, sel_node_ids_dict=selected,
-                                                         graph_sampler_args=graph_sampler_args, symm=symm)
+            if on_device:
+                selected, idx = devgraph.merge_node_ids_dict(requests, dev)
+                lookups[b] = dict(zip(names, idx))
+                needed, plans[b] = devgraph.gen_plan(self.encoders[b], graph, selected, graph_sampler_args, symm)
+            else:
+                selected, idx = merge_node_ids_dict(requests)
+                lookups[b] = dict(zip(names, idx))
+                needed, plans[b] = self.encoders[b].gen_plan(graph=graph, sel_node_ids_dict=selected,
+                                                             graph_sampler_args=graph_sampler_args, symm=symm)
         self.last_plans = (plans, lookups, needed)
 
         # ---- execution, first block first ----

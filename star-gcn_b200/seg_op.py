@@ -74,11 +74,15 @@ class Schedule:
         self.nnz = int(nnz)
         self.chunk = int(chunk)
         self.indptr = indptr
-        nbytes = lib.sg_plan_bytes(self.n_seg, self.nnz, self.chunk)
-        self.buf = _bytes(nbytes, indptr.device)
+        self.nbytes = lib.sg_plan_bytes(self.n_seg, self.nnz, self.chunk)
+        self.buf = _bytes(self.nbytes, indptr.device)
         self.partial_rows = int(lib.sg_plan_partial_rows(self.n_seg, self.nnz, self.chunk))
-        check(lib.sg_plan_build(_p(self.buf), nbytes, _p(indptr), self.n_seg, self.nnz, self.chunk, _stream()),
-              "sg_plan_build")
+        self.rebuild_()
+
+    def rebuild_(self):
+        """(Re)build the schedule from the current contents of ``indptr`` into the same buffer."""
+        check(_lib.load().sg_plan_build(_p(self.buf), self.nbytes, _p(self.indptr), self.n_seg, self.nnz, self.chunk,
+                                        _stream()), "sg_plan_build")
 
     def partial(self, K, F, extra_per_row=0):
         """Scratch for the partial rows of split segments.  Taken from the caching allocator on EVERY call, so

@@ -1,0 +1,122 @@
+"""Device plan maintenance (stargcn_b200.graph.MultiLinkCSR): construction from per-level lists without host
+concatenation, the sort-free transposed operands of a mutually transposed pair (bit-exact against the radix-sort
+path), and the in-place refresh + rebuild used by same-shaped iterations (CUDA-graph capturable)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def layer_lists(shape="ml-100k", seed=1000):
+    from stargcn_b200 import synth
+    return synth.make_layer_inputs(shape, seed=seed)
+
+
+def build(wl, side, **kw):
+    from stargcn_b200.graph import MultiLinkCSR
+    n_nb = wl["n_item"] if side == "user" else wl["n_user"]
+    return MultiLinkCSR(*wl[side][:3], n_nb=n_nb, device="cuda", **kw)
+
+
+def test_construction_from_numpy_pinned_and_device_lists_agree():
+    wl = layer_lists()
+    ep_l, ptr_l, sup_l = wl["user"][:3]
+    ref = build(wl, "user", validate=True)
+    want = np.concatenate(ep_l), np.concatenate(sup_l)
+    assert np.array_equal(ref.end_points.cpu().numpy(), want[0]) and np.array_equal(ref.support.cpu().numpy(), want[1])
+    offs = np.concatenate([[0], np.cumsum([int(p[-1]) for p in ptr_l])])
+    cat = np.concatenate([[0]] + [ptr_l[r][1:].astype(np.int64) + offs[r] for r in range(wl["R"])])
+    assert np.array_equal(ref.cat_indptr.cpu().numpy(), cat)
+    from stargcn_b200.graph import MultiLinkCSR
+    pinned = [[torch.from_numpy(a).pin_memory() for a in lst] for lst in (ep_l, ptr_l, sup_l)]
+    on_dev = [[torch.from_numpy(a).cuda() for a in lst] for lst in (ep_l, ptr_l, sup_l)]
+    for lists, kw in ((pinned, {}), (on_dev, {}), (on_dev, dict(nnz_l=[int(p[-1]) for p in ptr_l]))):
+        c = MultiLinkCSR(*lists, n_nb=wl["n_item"], device="cuda", **kw)
+        assert torch.equal(c.end_points, ref.end_points) and torch.equal(c.support, ref.support)
+        assert torch.equal(c.cat_indptr, ref.cat_indptr) and c.nnz_l == ref.nnz_l
+    # the reference's length-1 dummies for an empty level (graph.py:221-222) and the validation switch
+    ep2, sup2, ptr2 = list(ep_l), list(sup_l), list(ptr_l)
+    ep2[2], sup2[2], ptr2[2] = np.zeros(1, np.int32), np.zeros(1, np.float32), np.zeros_like(ptr_l[2])
+    c = MultiLinkCSR(ep2, ptr2, sup2, n_nb=wl["n_item"], device="cuda", validate=True)
+    assert c.nnz == ref.nnz - int(ptr_l[2][-1]) and c.nnz_l[2] == 0
+    bad = [e.copy() for e in ep_l]
+    bad[1][3] = wl["n_item"]
+    with pytest.raises(ValueError):
+        MultiLinkCSR(bad, ptr_l, sup_l, n_nb=wl["n_item"], device="cuda", validate=True)
+
+
+@pytest.mark.parametrize("shape", ["ml-100k", "ml-1m"])
+def test_transposed_operands_from_the_reverse_plan_are_bit_exact(shape):
+    wl = layer_lists(shape)
+    u_sort, i_sort = build(wl, "user"), build(wl, "item")
+    u_rev, i_rev = build(wl, "user"), build(wl, "item")
+    u_rev.set_reverse(i_rev)
+    i_rev.set_reverse(u_rev)
+    for a, b in ((u_sort, u_rev), (i_sort, i_rev)):
+        ta, tb = a.transposed(), b.transposed()
+        assert torch.equal(ta[0], tb[0]) and torch.equal(ta[1], tb[1])
+        # the weights are the plan's own (the two directions' supports differ in the last bit: (1/d_r)/d_c)
+        assert torch.equal(ta[2], tb[2])
+        assert b.reverse_mismatches() == 0
+    with pytest.raises(ValueError):
+        u_rev.set_reverse(u_sort)
+    # a pair that is NOT a pair of transposes is detected
+    from stargcn_b200.graph import MultiLinkCSR
+    ep_l, ptr_l, sup_l = wl["item"][:3]
+    ep_bad = [e.copy() for e in ep_l]
+    ep_bad[0][0] = (ep_bad[0][0] + 1) % wl["n_user"]
+    wrong = MultiLinkCSR(ep_bad, ptr_l, sup_l, n_nb=wl["n_user"], device="cuda")
+    u_chk = build(wl, "user").set_reverse(wrong)
+    u_chk.transposed()
+    assert u_chk.reverse_mismatches() > 0
+
+
+def test_refresh_in_place_and_graph_replay():
+    """load_lists_ + rebuild_ on a same-shaped plan: derived structures equal a freshly built plan, and a CUDA graph
+    that contains rebuild_ + forward + backward follows new list contents."""
+    from stargcn_b200 import runtime
+    from stargcn_b200.layers import MultiLinkGCNAggregator
+    wl = layer_lists()
+    R, D, U = wl["R"], wl["D"], 250
+    ep_l, ptr_l, sup_l = wl["user"][:3]
+    rs = np.random.RandomState(0)
+    # a second plan of the SAME shape: same pattern, permuted end points inside every segment is not needed —
+    # new supports and a rotation of the item ids keep every per-level count
+    ep_b = [((e.astype(np.int64) + 7) % wl["n_item"]).astype(np.int32) for e in ep_l]
+    sup_b = [rs.uniform(0.1, 1.0, s.shape).astype(np.float32) for s in sup_l]
+    csr = build(wl, "user").prepare(backward=True)
+    fresh_b = type(csr)(ep_b, ptr_l, sup_b, n_nb=wl["n_item"], device="cuda").prepare(backward=True)
+    agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", ordinal_sharing=False, accum="sum", in_units=D).cuda()
+    x = torch.randn(wl["n_item"], D, device="cuda").requires_grad_(True)
+    gout = torch.randn(wl["n_user"], U, device="cuda")
+    holder = {}
+
+    def step():
+        x.grad = None
+        for p in agg.parameters():
+            p.grad = None
+        csr.rebuild_()
+        out = agg(x, csr)
+        out.backward(gout)
+        holder["out"] = out.detach()
+
+    def reference(plan):
+        x2 = x.detach().clone().requires_grad_(True)
+        for p in agg.parameters():
+            p.grad = None
+        o = agg(x2, plan)
+        o.backward(gout)
+        return o.detach().clone(), x2.grad.clone(), agg.weight1.grad.clone()
+
+    want_a, want_b = reference(build(wl, "user")), reference(fresh_b)
+    graphed = runtime.GraphedStep(step)
+    graphed(); torch.cuda.synchronize()
+    assert torch.equal(holder["out"], want_a[0]) and torch.equal(x.grad, want_a[1]) and torch.equal(agg.weight1.grad, want_a[2])
+    pin = lambda lst: [torch.from_numpy(a).pin_memory() for a in lst]
+    csr.load_lists_(pin(ep_b), pin(ptr_l), pin(sup_b))
+    graphed(); torch.cuda.synchronize()
+    assert torch.equal(csr.transposed()[1], fresh_b.transposed()[1]) and torch.equal(csr.transposed()[2], fresh_b.transposed()[2])
+    assert torch.equal(holder["out"], want_b[0]) and torch.equal(x.grad, want_b[1]) and torch.equal(agg.weight1.grad, want_b[2])
+    with pytest.raises(ValueError):
+        csr.load_lists_(pin(ep_b)[:-1], pin(ptr_l)[:-1], pin(sup_b)[:-1])
