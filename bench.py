@@ -51,7 +51,10 @@ def parse_args():
     ap.add_argument("--check", action="store_true",
                     help="N>1: run the partitioned step over NCCL in both exchange modes (and on the strong partition) on a "
                          "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")
-    ap.add_argument("--presplit", action="store_true", help="A/B: round-1 GEMM path (operands pre-split in HBM)")
+    ap.add_argument("--inkernel-split", action="store_true",
+                    help="A/B: GEMM operands as plain fp32, split into TF32 hi/lo inside the kernel (default: pre-split by their producers)")
+    ap.add_argument("--copy-streams", type=int, default=3,
+                    help="e2e: extra CUDA streams the per-level list copies of a step are spread over (0: all on one copy stream)")
     ap.add_argument("--dev", action="append", default=[], metavar="NAME=VALUE",
                     help="development option of the library (sg_dev_option), e.g. gather_variant=1")
     return ap.parse_args()
@@ -455,8 +458,8 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if args.presplit:
-        graph.GEMM_INKERNEL_SPLIT = False
+    if args.inkernel_split:
+        graph.GEMM_INKERNEL_SPLIT = True
     for kv in args.dev:
         name, _, val = kv.partition("=")
         _lib.dev_option(name, int(val))
@@ -896,13 +899,13 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
     """Single-GPU end-to-end step for same-shaped plans (every training iteration of a full-neighbourhood run): two
     device slots, each with its OWN pair of MultiLinkCSR plans built once; per step the caller's pinned per-level
     lists and features are copied into the idle slot on a copy stream (``MultiLinkCSR.load_lists_``), then ONE CUDA
-    graph per slot re-derives the plan (``rebuild_``: schedules + transposed operands, the latter read off the reverse
-    direction's plan because the caller declared the two directions mutual transposes, ``set_reverse``) and runs
-    forward + backward of both directions on two streams; a scalar loss read-back ends the step."""
+    graph per slot re-derives the plan (``rebuild_``: schedules + stable transpose by radix sort) and runs forward +
+    backward of both directions on two streams; a scalar loss read-back ends the step."""
     import torch
     from stargcn_b200 import runtime
     from stargcn_b200.graph import MultiLinkCSR
     copy_stream = torch.cuda.Stream(device=dev)
+    extra_copy = [torch.cuda.Stream(device=dev) for _ in range(args.copy_streams)]
     main = torch.cuda.current_stream()
     slots = []
     for _ in range(2):
@@ -911,9 +914,8 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
             s = sides[side]
             csr = MultiLinkCSR(h["ep_l"], h["ptr_l"], h["sup_l"], n_nb=s["csr"].n_nb, device=dev)
             slot[side] = dict(csr=csr, x=torch.empty(h["x"].shape, dtype=torch.float32, device=dev).requires_grad_(True))
-        slot["user"]["csr"].set_reverse(slot["item"]["csr"])
-        slot["item"]["csr"].set_reverse(slot["user"]["csr"])
         for side in host:
+            slot[side]["csr"].keep_transpose_scratch = True
             slot[side]["csr"].prepare(backward=True)
         slots.append(slot)
     torch.cuda.synchronize()
@@ -941,7 +943,7 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
 
     def upload(slot):
         for side, h in host.items():
-            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"])
+            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"], copy_streams=extra_copy or None)
             with torch.no_grad():
                 slot[side]["x"].copy_(h["x"], non_blocking=True)
 
@@ -1008,9 +1010,8 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
                                note="copy-stream and compute-stream busy time per step (they overlap); the copy is the floor: "
                                     "PCIe moves the step's lists at the rate shown"),
                 includes="H2D of the 3*R per-level lists + features of both directions from pinned memory (double-buffered: the next "
-                "step's copy overlaps this step's compute), device-side concatenation, plan rebuild in the graph (schedules; transposed "
-                "operands derived from the reverse direction's plan — the caller declares the directions mutual transposes), the two "
-                "directions on two streams, fwd+bwd, scalar loss read-back")
+                "step's copy overlaps this step's compute), device-side concatenation, plan rebuild in the graph (schedules + stable "
+                "transpose), the two directions on two streams, fwd+bwd, scalar loss read-back")
 
 
 def main():

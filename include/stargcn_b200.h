@@ -49,7 +49,7 @@ void sg_launch_count_reset(void);
 /* Development only (tools/, A/B measurements): set a process-wide tuning option; 0 is always the shipped
  * behaviour and the product path never calls this.  Options: 0 gather variant (1 = bulk-copy staged segments),
  * 1 gather blocks per SM, 2 GEMM TMEM hand-back arrival (1 = release), 3 GEMM chain length in k-blocks,
- * 4 in-kernel split of a raw B operand.  Nothing in the library reads the environment. */
+ * 8 GEMM wait-cycle trace (sg_gemm_trace_read).  Nothing in the library reads the environment. */
 int sg_dev_option(int which, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -174,18 +174,6 @@ int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const f
 int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_perm,
                                   const int32_t *t_seg, const float *support, int R, int n_dst, int nnz,
                                   sg_stream_t stream);
-/* The same transposed operands WITHOUT a sort, from the plan of the REVERSE direction when the two plans are each
- * other's transpose (both directions of a full-neighbourhood bipartite layer; end points ascending inside every
- * segment): rev_* is the reverse direction's concatenated CSR (R * n_nb segments whose end points are this plan's
- * destination rows); the weights are this plan's own (found by binary search in its segment).  Bit-identical to
- * sg_csr_transpose + sg_multilink_transpose_finish on such a pair; *not_found (device) counts reverse edges the
- * plan does not hold (0 for a true pair).  ws needs sg_multilink_transpose_from_reverse_ws_bytes(n_nb) bytes. */
-size_t sg_multilink_transpose_from_reverse_ws_bytes(int n_nb);
-int sg_multilink_transpose_from_reverse(int32_t *t_indptr /*n_nb+1*/, int32_t *t_src /*nnz*/, float *t_w /*nnz*/,
-                                        int32_t *not_found /*1*/, const int32_t *rev_end_points,
-                                        const int32_t *rev_cat_indptr /*R*n_nb+1*/, const int32_t *end_points,
-                                        const int32_t *cat_indptr /*R*n_dst+1*/, const float *support, int R, int n_dst,
-                                        int n_nb, int nnz, void *ws, sg_stream_t stream);
 int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, const float *t_w,
                          const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
                          int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,
@@ -338,6 +326,9 @@ int sg_multi_adam(float *const *params, float *const *grads, float *const *ms, f
  * weight or epilogue — and write one row: out[blocks * 16, 64].  Bytes moved =
  * blocks * 16 * reads_per_group * 256.
  * ---------------------------------------------------------------------------------------- */
+/* Development: with dev option 8 (gemm_trace) set, the GEMM kernels accumulate the cycles the roles of one CTA pair
+ * spend waiting; this copies the 8 counters to the host and clears them (synchronises the device). */
+int sg_gemm_trace_read(unsigned long long *host8);
 /* Measurement aid: TMA delivery rate to one SM — `blocks` CTAs each stream `iters` ring slots of `boxes`
  * [32 floats x 128 rows] boxes (16 KB each) of src[rows, K] (ld floats per row) through `stages` slots.
  * Bytes moved = blocks * |iters| * boxes * 16384; iters < 0: every CTA reads the SAME boxes (hot L2 lines, the

@@ -71,8 +71,7 @@ SIGNATURES = {
     "sg_colsum": (_c_int, [_c_p] * 3 + [_c_int] * 3 + [_c_p, _c_p]),
     "sg_split_tf32": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_int, _c_int, _c_int, _c_int, _c_p]),
     "sg_act_bwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_int, _c_int, ctypes.c_float, _c_p]),
-    "sg_multilink_transpose_from_reverse_ws_bytes": (_c_sz, [_c_int]),
-    "sg_multilink_transpose_from_reverse": (_c_int, [_c_p] * 9 + [_c_int] * 4 + [_c_p, _c_p]),
+    "sg_gemm_trace_read": (_c_int, [_c_p]),
     "sg_tma_probe": (_c_int, [_c_p] + [_c_int] * 7 + [_c_p]),
     "sg_row_gather_probe": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, ctypes.c_uint, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),
@@ -114,7 +113,7 @@ def check(rc, what):
         raise StarGCNError(f"{what} failed (code {rc}): {msg}")
 
 
-DEV_OPTIONS = {"gather_variant": 0, "gather_grid": 1, "gemm_arrive": 2, "gemm_chain": 3, "gemm_split_b": 4, "gemm_a_block_rows": 5, "gemm_split_exp": 6, "gemm_producers": 7}
+DEV_OPTIONS = {"gather_variant": 0, "gather_grid": 1, "gemm_arrive": 2, "gemm_chain": 3, "gemm_trace": 8}
 
 
 def dev_option(name, value):

@@ -57,11 +57,8 @@ enum DevOption {
   SG_DEV_GATHER_GRID = 1,      // blocks per SM of the grid-stride gather launches (0 = 32)
   SG_DEV_GEMM_ARRIVE = 2,      // 1: cluster-scope RELEASE arrival when a TMEM buffer is handed back (0 = relaxed)
   SG_DEV_GEMM_CHAIN = 3,       // k-blocks per TMEM accumulation chain (0 = kChainKBlocks)
-  SG_DEV_GEMM_SPLIT_B = 4,     // in-kernel-split GEMM, K-major: 1 = also split B in the kernel when it arrives raw
-  SG_DEV_GEMM_A_BLOCK_ROWS = 5, // EXPERIMENT: K-major A operand stored k-block-major [kb][rows][32] with this many rows per block
-  SG_DEV_GEMM_SPLIT_EXP = 6,    // EXPERIMENT (timing only, wrong results): 1 relaxed split arrival, 2 no proxy fence, 4 no split work
-  SG_DEV_GEMM_PRODUCERS = 7,    // 1: the single-producer-warp pair kernel of round 1 (A/B); 0 = four TMA producer warps
-  SG_DEV_COUNT = 8
+  SG_DEV_GEMM_TRACE = 8,        // 1: accumulate wait cycles of pair 0's leader CTA (sg_gemm_trace_read)
+  SG_DEV_COUNT = 12
 };
 int dev_option(int which);
 

@@ -46,9 +46,20 @@ struct GemmArgs {
   int epi;           // 0 store, 1 leaky (slope)
   float slope;
   const float *bias; // optional [N], added before the activation
-  int split_exp;      // experiment bits (SG_DEV_GEMM_SPLIT_EXP)
-  int a_block_rows;   // experiment: > 0 = K-major A stored k-block-major, this many rows per block
+  int trace;          // development: accumulate wait cycles of pair 0's leader into g_gemm_trace
   int relaxed_arrive; // hand the TMEM buffer back with a relaxed arrival (default; see mbar_arrive_leader_relaxed)
+};
+
+// Development trace (SG_DEV_GEMM_TRACE): cycles the roles of the LEADER CTA of pair 0 spend waiting, summed over the
+// launch — [0] MMA thread on full_bar, [1] MMA thread on tmem_empty, [2] MMA thread total, [3] producer 0 on
+// empty_bar, [4] producer 0 total, [5] epilogue warp on tmem_full, [6] epilogue warp total, [7] k-blocks.
+__device__ unsigned long long g_gemm_trace[8];
+struct TraceClock {
+  long long t0;
+  bool on;
+  __device__ __forceinline__ TraceClock(bool enabled) : t0(0), on(enabled) {}
+  __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+  __device__ __forceinline__ void end(int slot) { if (on) atomicAdd(&g_gemm_trace[slot], (unsigned long long)(clock64() - t0)); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -263,6 +274,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  TraceClock trc(g.trace && pair_id == 0 && leader && lane == 0 && (warp == 0 || warp == 1 || warp == 2));
+  const long long trc_start = trc.on ? clock64() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -276,7 +289,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
           const int s = v % STAGES;
           const uint32_t ph = (v / STAGES) & 1;
+          trc.begin();
           mbar_wait(&empty_bar[s], ph ^ 1);
+          trc.end(3);
           if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // bytes of BOTH CTAs
           uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
           if constexpr (MN_MAJOR) {
@@ -288,9 +303,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               tma_load_2d_pair(sb_lo + a * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + a * 32, kb * kBK);
             }
           } else {
-            const int ac0 = g.a_block_rows ? 0 : kb * kBK, ac1 = g.a_block_rows ? kb * g.a_block_rows + m0 : m0;
-            tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], ac0, ac1);
-            tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], ac0, ac1);
+            tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
+            tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
             tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
             tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
           }
@@ -307,16 +321,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         const int n_kb = kb_end - kb_begin;
         const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
         const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        // chains of a tile are balanced (21 k-blocks -> 4+4+4+3+3+3, not 4x5+1): a one-k-block tail chain finishes
+        // before the buffer of the chain before the previous one has been drained and stalls the MMA warp
+        const int n_chains = (n_kb + g.chain_kb - 1) / g.chain_kb;
+        const int len_lo = n_kb / n_chains, n_long = n_kb - len_lo * n_chains;   // the first n_long chains have len_lo + 1
+        int vin = 0, clen = len_lo + (n_long > 0 ? 1 : 0), cidx = 0;
         for (int i = 0; i < n_kb; ++i, ++v) {
           const int s = v % STAGES;
           const uint32_t ph = (v / STAGES) & 1;
-          const int vin = i % g.chain_kb;
           const int buf = chain & 1;
           if (vin == 0) {
+            trc.begin();
             mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            trc.end(1);
             tc_fence_after();
           }
+          trc.begin();
           mbar_wait(&full_bar[s], ph);
+          trc.end(0);
           tc_fence_after();
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
                          sb_lo = sb_hi + B_BYTES;
@@ -337,9 +359,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             }
           }
           umma_commit_pair(&empty_bar[s]);
-          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
+          if (trc.on) atomicAdd(&g_gemm_trace[7], 1ull);
+          if (++vin == clen) {
             umma_commit_pair(&tmem_full_bar[buf]);
             ++chain;
+            ++cidx;
+            vin = 0;
+            clen = len_lo + (cidx < n_long ? 1 : 0);
           }
         }
       }
@@ -361,7 +387,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
       for (int c = 0; c < n_chains; ++c, ++chain) {
         const int buf = chain & 1;
+        trc.begin();
         mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
+        trc.end(5);
         tc_fence_after();
         if (active) {
 #pragma unroll
@@ -393,16 +421,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
           __syncwarp();
           const int rows = min(32, g.M - row0);
-          for (int rr = 0; rr < rows; ++rr) {
+          const bool col_ok = col < g.N;
+          float *dcol = dbase + (long long)row0 * g.ldd + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {      // unrolled: 8 independent smem reads / row stores in flight
             float x = stg[rr * 33 + lane] + bias;
             if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
-            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+            if (col_ok && rr < rows) dcol[(long long)rr * g.ldd] = x;
           }
           __syncwarp();
         }
       }
     }
   }
+  if (trc.on) atomicAdd(&g_gemm_trace[warp == 1 ? 2 : (warp == 0 ? 4 : 6)], (unsigned long long)(clock64() - trc_start));
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -411,219 +443,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// The same CTA-pair kernel with FOUR TMA producer warps.
-//
-// What bounded the kernel above is not the memory system but the single issuing thread: a thread that issues
-// [32 floats x 128 rows] boxes delivers 35 / 48 / 57 GB/s per SM at 1 / 2 / 4 boxes per barrier phase no matter
-// how many stages are in flight or whether the source sits in L2 or DRAM (t = 0.24 us + 0.23 us per box), while
-// two / four issuing WARPS reach 87 / 132 GB/s per SM on the same ring (tools/gemm_bench.py, sg_tma_probe;
-// profiles/r02_summary.md).  A 64 KB stage (A_hi, A_lo, B_hi, B_lo) took 1.15 us to issue against 0.84 us of
-// tensor work.  Here each of the four operand tiles of a stage has its own producer warp (MN-major: each warp
-// issues one of the four 32-column atoms of all four tiles), and the warp-group register budgets of the split
-// kernel below pay for the extra warps: WG0 = 4 producers (40), WG1-2 = 8 epilogue warps (208), WG3 = MMA warp,
-// TMEM allocator, 2 idle (56).
-// ---------------------------------------------------------------------------------------------
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-constexpr int kPair4Threads = 512;
-
-template <int STAGES, bool MN_MAJOR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPair4Threads, 1)
-    tf32x3_gemm_pair4_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                             const GemmArgs g) {
-  constexpr int BN = 256;
-  constexpr int A_BYTES = kBM * kBK * 4;
-  constexpr int B_BYTES = 128 * kBK * 4;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr int STG_FLOATS = 32 * 33;
-  constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
-                                  ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(256 >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float *stg_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
-  __shared__ uint64_t full_bar[STAGES];    // leader only: TMA bytes of both CTAs (one arrival: the leader's producer 0)
-  __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t tmem_full_bar[2];
-  __shared__ uint64_t tmem_empty_bar[2];   // leader only
-  __shared__ uint32_t tmem_base_smem;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int tiles_n = g.tiles_n, tiles_mn = g.tiles_m * g.tiles_n;
-  const int n_tiles = tiles_mn * g.splits;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
-    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
-  }
-  if (warp == 12 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
-    fence_barrier_init();
-  }
-  if (warp == 13) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-
-  if (warp < 4) {
-    // ---- four TMA producer warps (both CTAs): warp p owns operand tile p (K-major) / atom p of every tile (MN-major) ----
-    reg_dec<40>();
-    if (lane == 0) {
-      const int p = warp;
-      int v = 0;
-      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
-        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-        const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
-        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
-        const int nb0 = n0 + (int)rank * (n_eff >> 1);
-        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++v) {
-          const int s = v % STAGES;
-          const uint32_t ph = (v / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader && p == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // the ONE arrival; bytes of both CTAs
-          uint8_t *sa_hi = smem + s * STAGE_BYTES, *sa_lo = sa_hi + A_BYTES, *sb_hi = sa_lo + A_BYTES, *sb_lo = sb_hi + B_BYTES;
-          if constexpr (MN_MAJOR) {
-            tma_load_2d_pair(sa_hi + p * (kBK * 128), &map_a_hi, &full_bar[s], m0 + p * 32, kb * kBK);
-            tma_load_2d_pair(sa_lo + p * (kBK * 128), &map_a_lo, &full_bar[s], m0 + p * 32, kb * kBK);
-            tma_load_2d_pair(sb_hi + p * (kBK * 128), &map_b_hi, &full_bar[s], nb0 + p * 32, kb * kBK);
-            tma_load_2d_pair(sb_lo + p * (kBK * 128), &map_b_lo, &full_bar[s], nb0 + p * 32, kb * kBK);
-          } else {
-            if (p == 0) tma_load_2d_pair(sa_hi, &map_a_hi, &full_bar[s], kb * kBK, m0);
-            else if (p == 1) tma_load_2d_pair(sa_lo, &map_a_lo, &full_bar[s], kb * kBK, m0);
-            else if (p == 2) tma_load_2d_pair(sb_hi, &map_b_hi, &full_bar[s], kb * kBK, nb0);
-            else tma_load_2d_pair(sb_lo, &map_b_lo, &full_bar[s], kb * kBK, nb0);
-          }
-        }
-      }
-    }
-  } else if (warp >= 12) {
-    reg_dec<56>();
-    if (warp == 12 && leader && lane == 0) {
-      int v = 0, chain = 0;
-      for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
-        const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-        const int n0 = (rem % tiles_n) * BN;
-        const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-        const int n_kb = kb_end - kb_begin;
-        const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
-        const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
-        for (int i = 0; i < n_kb; ++i, ++v) {
-          const int s = v % STAGES;
-          const uint32_t ph = (v / STAGES) & 1;
-          const int vin = i % g.chain_kb;
-          const int buf = chain & 1;
-          if (vin == 0) {
-            mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES), sa_lo = sa_hi + A_BYTES, sb_hi = sa_lo + A_BYTES,
-                         sb_lo = sb_hi + B_BYTES;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // hi.hi, hi.lo, lo.hi
-            const uint32_t sa = pass == 2 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
-#pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              uint64_t da, db;
-              if constexpr (MN_MAJOR) {
-                da = make_smem_desc(sa + k * 1024, kBK * 128, 512, 1);
-                db = make_smem_desc(sb + k * 1024, kBK * 128, 512, 1);
-              } else {
-                da = make_smem_desc(sa + k * 32, 16, 1024, 2);
-                db = make_smem_desc(sb + k * 32, 16, 1024, 2);
-              }
-              umma_tf32_pair(tmem_base + (uint32_t)(buf * BN), da, db, idesc, (vin != 0) || (pass != 0) || (k != 0));
-            }
-          }
-          umma_commit_pair(&empty_bar[s]);
-          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
-            umma_commit_pair(&tmem_full_bar[buf]);
-            ++chain;
-          }
-        }
-      }
-    }
-  } else {
-    // ---- epilogue warps 4..11 ----
-    reg_inc<208>();
-    const int q = warp & 3;
-    const int h = (warp - 4) >> 2;
-    const int cbase = h * (BN / 2);
-    float *stg = stg_all + (warp - 4) * STG_FLOATS;
-    int chain = 0;
-    for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
-      const int z = tile / tiles_mn, rem = tile - z * tiles_mn;
-      const int m0 = (rem / tiles_n) * 256 + (int)rank * kBM, n0 = (rem % tiles_n) * BN;
-      const int kb_begin = z * g.kb_per_split, kb_end = min(kb_begin + g.kb_per_split, g.kb_total);
-      const int n_chains = (kb_end - kb_begin + g.chain_kb - 1) / g.chain_kb;
-      const bool active = n0 + cbase < g.N && m0 < g.M;  // warp-uniform
-      float racc[BN / 2];
-#pragma unroll
-      for (int j = 0; j < BN / 2; ++j) racc[j] = 0.f;
-      for (int c = 0; c < n_chains; ++c, ++chain) {
-        const int buf = chain & 1;
-        mbar_wait(&tmem_full_bar[buf], (chain >> 1) & 1);
-        tc_fence_after();
-        if (active) {
-#pragma unroll
-          for (int ch = 0; ch < BN / 2 / 32; ++ch) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + ch * 32), r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(r[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (g.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty_bar[buf]);
-          else mbar_arrive_leader(&tmem_empty_bar[buf]);
-        }
-      }
-      if (active) {
-        float *dbase = g.D + (long long)z * g.split_stride;
-        const int row0 = m0 + q * 32;
-#pragma unroll
-        for (int ch = 0; ch < BN / 2 / 32; ++ch) {
-          const int col = n0 + cbase + ch * 32 + lane;
-          if (n0 + cbase + ch * 32 >= g.N) break;
-          float bias = 0.f;
-          if (g.bias && col < g.N) bias = __ldg(g.bias + col);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
-          __syncwarp();
-          const int rows = min(32, g.M - row0);
-          for (int rr = 0; rr < rows; ++rr) {
-            float x = stg[rr * 33 + lane] + bias;
-            if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
-            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 13) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // CTA-pair kernel with the hi/lo operand split done INSIDE the kernel.
@@ -782,14 +603,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
         const int n_kb = kb_end - kb_begin;
         const int n_eff = min(BN, ((g.N - n0) + 15) & ~15);
         const uint32_t idesc = IDESC_BASE | ((uint32_t)(n_eff >> 3) << 17);
+        // chains of a tile are balanced (21 k-blocks -> 4+4+4+3+3+3, not 4x5+1): a one-k-block tail chain finishes
+        // before the buffer of the chain before the previous one has been drained and stalls the MMA warp
+        const int n_chains = (n_kb + g.chain_kb - 1) / g.chain_kb;
+        const int len_lo = n_kb / n_chains, n_long = n_kb - len_lo * n_chains;   // the first n_long chains have len_lo + 1
+        int vin = 0, clen = len_lo + (n_long > 0 ? 1 : 0), cidx = 0;
         for (int i = 0; i < n_kb; ++i, ++v) {
           const int s = v % STAGES;
           const uint32_t ph = (v / STAGES) & 1;
-          const int vin = i % g.chain_kb;
           const int buf = chain & 1;
           if (vin == 0) {
-            if (g.split_exp & 8) mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
-            else mbar_wait_cluster(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
+            mbar_wait_cluster(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1);
             tc_fence_after();
           }
           mbar_wait(&full_bar[s], ph);
@@ -800,8 +624,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
           for (int pass = 0; pass < 3; ++pass) {  // hi.hi, hi.lo, lo.hi
             // the raw tiles are the hi operands; a pre-split B_lo arrives by TMA, everything else "lo" by the splitters
             if ((pass == 1 && SPLIT_B) || (pass == 2 && !SPLIT_B)) {
-              if (g.split_exp & 8) mbar_wait(&split_bar[s], ph);
-              else mbar_wait_cluster(&split_bar[s], ph);
+              mbar_wait_cluster(&split_bar[s], ph);
               tc_fence_after();
             }
             const uint32_t sa = pass == 2 ? sa_lo : sa_hi, sb = pass == 1 ? sb_lo : sb_hi;
@@ -819,9 +642,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
             }
           }
           umma_commit_pair(&empty_bar[s]);
-          if (vin == g.chain_kb - 1 || i == n_kb - 1) {
+          if (++vin == clen) {
             umma_commit_pair(&tmem_full_bar[buf]);
             ++chain;
+            ++cidx;
+            vin = 0;
+            clen = len_lo + (cidx < n_long ? 1 : 0);
           }
         }
       }
@@ -844,16 +670,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
           mbar_wait_cluster(&go_bar[s], ph);
         }
         uint8_t *sa_hi = smem + s * STAGE_BYTES;
-        if (!(g.split_exp & 4)) {
-          split_tile_16k(sa_hi, sa_hi + A_BYTES, st);
-          if constexpr (SPLIT_B) split_tile_16k(sa_hi + 2 * A_BYTES, sa_hi + 2 * A_BYTES + B_BYTES, st);
-        }
-        if (!(g.split_exp & 2)) fence_proxy_async_smem();
+        split_tile_16k(sa_hi, sa_hi + A_BYTES, st);
+        if constexpr (SPLIT_B) split_tile_16k(sa_hi + 2 * A_BYTES, sa_hi + 2 * A_BYTES + B_BYTES, st);
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          if (g.split_exp & 1) mbar_arrive_leader_relaxed(&split_bar[s]);
-          else mbar_arrive_leader(&split_bar[s]);
-        }
+        if (lane == 0) mbar_arrive_leader(&split_bar[s]);
       }
     }
   } else {
@@ -907,10 +728,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSplitThreads, 1)
           for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = racc[ch * 32 + j];
           __syncwarp();
           const int rows = min(32, g.M - row0);
-          for (int rr = 0; rr < rows; ++rr) {
+          const bool col_ok = col < g.N;
+          float *dcol = dbase + (long long)row0 * g.ldd + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {      // unrolled: 8 independent smem reads / row stores in flight
             float x = stg[rr * 33 + lane] + bias;
             if (g.epi == 1) x = x > 0.f ? x : g.slope * x;
-            if (col < g.N) dbase[(long long)(row0 + rr) * g.ldd + col] = x;
+            if (col_ok && rr < rows) dcol[(long long)rr * g.ldd] = x;
           }
           __syncwarp();
         }
@@ -1116,21 +940,6 @@ static int launch_gemm_pair(const CUtensorMap (&maps)[4], GemmArgs g, int splits
   return SG_OK;
 }
 
-template <int STAGES, bool MN>
-static int launch_gemm_pair4(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
-  constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
-  SG_CUDA(cudaFuncSetAttribute(tf32x3_gemm_pair4_kernel<STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  g.tiles_m = ceil_div(g.M, 256);
-  g.tiles_n = ceil_div(g.N, 256);
-  g.splits = splits;
-  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * splits;
-  const int max_pairs = num_sms() / 2;
-  const int pairs = (int)(n_tiles < max_pairs ? n_tiles : max_pairs);
-  tf32x3_gemm_pair4_kernel<STAGES, MN><<<2 * pairs, kPair4Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-  SG_LAUNCHED("tf32x3_gemm_pair4_kernel");
-  return SG_OK;
-}
-
 template <int STAGES, bool MN, bool SPLIT_B>
 static int launch_gemm_split(const CUtensorMap (&maps)[4], GemmArgs g, int splits, cudaStream_t st) {
   constexpr int smem = STAGES * 2 * (kBM * kBK * 4 + 128 * kBK * 4) + kEpiWarps * 32 * 33 * 4 + 1024;
@@ -1181,8 +990,7 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
   g.M = M; g.N = N; g.epi = epilogue; g.slope = slope; g.bias = bias;
   g.chain_kb = dev_option(SG_DEV_GEMM_CHAIN) > 0 ? dev_option(SG_DEV_GEMM_CHAIN) : kChainKBlocks;
   g.relaxed_arrive = dev_option(SG_DEV_GEMM_ARRIVE) == 0;
-  g.a_block_rows = (!mn_major && A_lo) ? dev_option(SG_DEV_GEMM_A_BLOCK_ROWS) : 0;
-  g.split_exp = dev_option(SG_DEV_GEMM_SPLIT_EXP);
+  g.trace = dev_option(SG_DEV_GEMM_TRACE);
   g.kb_total = ceil_div(K, kBK);
   g.kb_per_split = ceil_div(g.kb_total, splits);
   splits = ceil_div(g.kb_total, g.kb_per_split);  // no empty split
@@ -1197,28 +1005,31 @@ int sg_gemm_tf32x3(float *D, int ldd, const float *A_hi, const float *A_lo, int 
     if ((rc = make_map_mnmajor(&maps[2], B_hi, K, N, ldb)) != SG_OK) return rc;
     if ((rc = make_map_mnmajor(&maps[3], B_lo ? B_lo : B_hi, K, N, ldb)) != SG_OK) return rc;
     if (!A_lo) rc = B_lo ? launch_gemm_split<3, true, false>(maps, g, splits, st) : launch_gemm_split<3, true, true>(maps, g, splits, st);
-    else rc = dev_option(SG_DEV_GEMM_PRODUCERS) == 1 ? launch_gemm_pair<3, true>(maps, g, splits, st)
-                                                     : launch_gemm_pair4<3, true>(maps, g, splits, st);
+    else rc = launch_gemm_pair<3, true>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   } else {
-    if (g.a_block_rows > 0) {   // [kb][rows][32]: a matrix of 32 columns and kb_total * rows rows
-      if ((rc = make_map_kmajor(&maps[0], A_hi, g.kb_total * g.a_block_rows, kBK, kBK, kBM)) != SG_OK) return rc;
-      if ((rc = make_map_kmajor(&maps[1], A_lo, g.kb_total * g.a_block_rows, kBK, kBK, kBM)) != SG_OK) return rc;
-    } else {
-      if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
-      if ((rc = make_map_kmajor(&maps[1], A_lo ? A_lo : A_hi, M, K, lda, kBM)) != SG_OK) return rc;
-    }
+    if ((rc = make_map_kmajor(&maps[0], A_hi, M, K, lda, kBM)) != SG_OK) return rc;
+    if ((rc = make_map_kmajor(&maps[1], A_lo ? A_lo : A_hi, M, K, lda, kBM)) != SG_OK) return rc;
     if ((rc = make_map_kmajor(&maps[2], B_hi, N, K, ldb, 128)) != SG_OK) return rc;   // a CTA of a pair loads half of the B tile
     if ((rc = make_map_kmajor(&maps[3], B_lo ? B_lo : B_hi, N, K, ldb, 128)) != SG_OK) return rc;
     if (!A_lo) rc = B_lo ? launch_gemm_split<3, false, false>(maps, g, splits, st) : launch_gemm_split<3, false, true>(maps, g, splits, st);
-    else rc = dev_option(SG_DEV_GEMM_PRODUCERS) == 1 ? launch_gemm_pair<3, false>(maps, g, splits, st)
-                                                     : launch_gemm_pair4<3, false>(maps, g, splits, st);
+    else rc = launch_gemm_pair<3, false>(maps, g, splits, st);
     if (rc != SG_OK) return rc;
   }
   if (splits > 1) {
     splitk_reduce_kernel<<<grid_ew((long long)M * N), 256, 0, st>>>(D, ldd, split_ws, M, N, splits);
     SG_LAUNCHED("splitk_reduce_kernel");
   }
+  return SG_OK;
+}
+
+/* Development: copy the 8 trace counters (see g_gemm_trace) to the host and clear them.  Synchronises the device. */
+int sg_gemm_trace_read(unsigned long long *host8) {
+  SG_REQUIRE(host8, "sg_gemm_trace_read: null pointer");
+  SG_CUDA(cudaDeviceSynchronize());
+  SG_CUDA(cudaMemcpyFromSymbol(host8, g_gemm_trace, 8 * sizeof(unsigned long long)));
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  SG_CUDA(cudaMemcpyToSymbol(g_gemm_trace, zero, sizeof(zero)));
   return SG_OK;
 }
 

@@ -320,69 +320,6 @@ __global__ void __launch_bounds__(256) multilink_finish(int32_t *__restrict__ t_
 }
 
 // ------------------------------------------------------------------------------------------
-// Transposed pattern WITHOUT a sort, for a pair of plans that are each other's transpose (both directions of a
-// full-neighbourhood bipartite layer: the user<-item CSR lists, per (level r, user u), the items j; the item<-user
-// CSR lists, per (r, j), the users u — the same edge set).  The stable transpose of the first plan groups its
-// positions by item j in ascending position order, i.e. by (r, u): exactly the reverse plan's segments (0, j),
-// (1, j), ... (R-1, j) laid end to end (ids inside a segment are ascending).  So
-//     t_indptr[j]            = sum over j' < j and all r of len(rev segment (r, j'))
-//     t_src of (r, j)        = rev end points * R + r, at t_indptr[j] + sum_{r' < r} len(rev (r', j))
-// Two small kernels + one scan replace iota + radix sort + two permutation gathers (~0.35 ms -> ~0.05 ms per
-// direction at the ML-10M shape).  The edge weight is looked up in the plan's OWN segment (r, u) by binary search for
-// j — the two directions' weights differ in the last bit (get_support evaluates (1/d_row)/d_col,
-// graph_sampler.cpp:408-412, and row / column swap roles) — so the result is bit-identical to the sorted path.
-// Edges of the reverse plan that the plan itself does not hold are counted in `not_found` (the pair was not a pair
-// of transposes).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reverse_row_totals(int32_t *__restrict__ tot, const int32_t *__restrict__ rev_ptr,
-                                                          int R, int n_rows) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += gridDim.x * blockDim.x) {
-    int t = 0;
-    for (int r = 0; r < R; ++r) {
-      const long long s = (long long)r * n_rows + j;
-      t += __ldg(rev_ptr + s + 1) - __ldg(rev_ptr + s);
-    }
-    tot[j] = t;
-  }
-}
-
-__global__ void __launch_bounds__(256) reverse_scatter(int32_t *__restrict__ t_src, float *__restrict__ t_w,
-                                                       const int32_t *__restrict__ t_indptr, const int32_t *__restrict__ rev_ep,
-                                                       const int32_t *__restrict__ rev_ptr, const int32_t *__restrict__ own_ep,
-                                                       const int32_t *__restrict__ own_ptr, const float *__restrict__ own_w,
-                                                       int R, int n_rows, int n_dst, int32_t *__restrict__ not_found) {
-  constexpr int LANES = 8;                 // one lane group per reverse segment (r, j)
-  const int lane = threadIdx.x & (LANES - 1);
-  const long long n_seg = (long long)R * n_rows;
-  for (long long seg = (long long)(blockIdx.x * blockDim.x + threadIdx.x) / LANES; seg < n_seg;
-       seg += (long long)gridDim.x * blockDim.x / LANES) {
-    const int r = (int)(seg / n_rows), j = (int)(seg - (long long)r * n_rows);
-    int base = __ldg(t_indptr + j);
-    for (int q = 0; q < r; ++q) {
-      const long long s = (long long)q * n_rows + j;
-      base += __ldg(rev_ptr + s + 1) - __ldg(rev_ptr + s);
-    }
-    const int q0 = __ldg(rev_ptr + seg), q1 = __ldg(rev_ptr + seg + 1);
-    for (int q = q0 + lane; q < q1; q += LANES) {
-      const int u = __ldg(rev_ep + q);
-      // the weight is THIS plan's weight of edge (r, u) -> j: find j in the plan's own segment (r, u) (ids ascending)
-      const long long own_seg = (long long)r * n_dst + u;
-      int lo = __ldg(own_ptr + own_seg), hi = __ldg(own_ptr + own_seg + 1);
-      const int end = hi;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(own_ep + mid) < j) lo = mid + 1; else hi = mid;
-      }
-      float w = 0.f;
-      if (lo < end && __ldg(own_ep + lo) == j) w = __ldg(own_w + lo);
-      else atomicAdd(not_found, 1);
-      t_src[base + (q - q0)] = u * R + r;
-      t_w[base + (q - q0)] = w;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // unique + inverse in FIRST-OCCURRENCE order: the serial, order-defining
 // unique_inverse of GraphSampler/graph_sampler.h:510-534 that merge_nodes / gen_plan use to turn
 // node ids into local row indices (mxgraph/graph.py:142-163, layers.py:308-334).
@@ -578,33 +515,6 @@ int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_p
   SG_REQUIRE(t_src && t_w && t_perm && t_seg && support, "sg_multilink_transpose_finish: null pointer");
   multilink_finish<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(t_src, t_w, t_perm, t_seg, support, R, n_dst, nnz);
   SG_LAUNCHED("multilink_finish");
-  return SG_OK;
-}
-
-size_t sg_multilink_transpose_from_reverse_ws_bytes(int n_nb) { return scan_ws_bytes(n_nb > 0 ? n_nb : 1) + 128; }
-
-int sg_multilink_transpose_from_reverse(int32_t *t_indptr, int32_t *t_src, float *t_w, int32_t *not_found,
-                                        const int32_t *rev_end_points, const int32_t *rev_cat_indptr,
-                                        const int32_t *end_points, const int32_t *cat_indptr, const float *support,
-                                        int R, int n_dst, int n_nb, int nnz, void *ws, sg_stream_t stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  SG_REQUIRE(R > 0 && n_nb >= 0 && n_dst >= 0 && nnz >= 0, "sg_multilink_transpose_from_reverse: bad sizes");
-  SG_REQUIRE((long long)R * n_nb < (1LL << 31) && (long long)R * n_dst < (1LL << 31),
-             "sg_multilink_transpose_from_reverse: R*n overflows int32");
-  SG_REQUIRE(t_indptr && not_found && rev_cat_indptr && cat_indptr && ws &&
-             (nnz == 0 || (t_src && t_w && rev_end_points && end_points && support)),
-             "sg_multilink_transpose_from_reverse: null pointer");
-  SG_CUDA(cudaMemsetAsync(not_found, 0, sizeof(int32_t), st));
-  if (n_nb == 0) { SG_CUDA(cudaMemsetAsync(t_indptr, 0, sizeof(int32_t), st)); return SG_OK; }
-  reverse_row_totals<<<grid_for(n_nb), 256, 0, st>>>(t_indptr, rev_cat_indptr, R, n_nb);
-  SG_LAUNCHED("reverse_row_totals");
-  int rc = exclusive_scan_i32(t_indptr, t_indptr, n_nb, t_indptr + n_nb, ws, st);   // total -> t_indptr[n_nb]
-  if (rc != SG_OK) return rc;
-  if (nnz > 0) {
-    reverse_scatter<<<grid_for((long long)R * n_nb * 8), 256, 0, st>>>(t_src, t_w, t_indptr, rev_end_points, rev_cat_indptr,
-                                                                       end_points, cat_indptr, support, R, n_nb, n_dst, not_found);
-    SG_LAUNCHED("reverse_scatter");
-  }
   return SG_OK;
 }
 

@@ -103,16 +103,19 @@ class MultiLinkCSR:
         self._init_device(ep_cat, sup_cat, cat_indptr, chunk, use_schedule)
         self._ptr2, self._offs_dev, self._offs = ptr2, offs_dev, offs
 
-    def load_lists_(self, end_points_l, indptr_l, support_l):
+    def load_lists_(self, end_points_l, indptr_l, support_l, copy_streams=None):
         """Refresh the plan IN PLACE from new per-level lists with the SAME per-level edge counts (same-shaped plan
         of the next iteration): every level is copied straight into its slice of the existing device arrays
         (asynchronously from pinned memory) and the concatenated indptr is re-assembled on the device.  The derived
-        structures are stale afterwards — call :meth:`rebuild_` (CUDA-graph capturable) before the next use."""
+        structures are stale afterwards — call :meth:`rebuild_` (CUDA-graph capturable) before the next use.
+        ``copy_streams``: optional list of extra CUDA streams; the 3*R copies are spread over them so that the
+        per-copy DMA set-up of one overlaps the transfer of another (they fork from and join the current stream)."""
         if getattr(self, "_ptr2", None) is None:
             raise ValueError("load_lists_ needs a plan that was built from per-level lists")
         R, n_dst, offs = self.R, self.n_dst, self._offs
         if not (len(end_points_l) == len(indptr_l) == len(support_l) == R):
             raise ValueError("the refreshed lists must have the same number of levels")
+        jobs = []
         for r in range(R):
             n = self.nnz_l[r]
             e, s_, p = (_as_tensor(end_points_l[r], torch.int32), _as_tensor(support_l[r], torch.float32),
@@ -120,9 +123,25 @@ class MultiLinkCSR:
             if p.shape[0] != n_dst + 1 or e.shape[0] < n or s_.shape[0] < n:
                 raise ValueError(f"level {r}: shape differs from the plan being refreshed")
             if n:
-                self.end_points[offs[r]:offs[r + 1]].copy_(e[:n], non_blocking=True)
-                self.support[offs[r]:offs[r + 1]].copy_(s_[:n], non_blocking=True)
-            self._ptr2[r].copy_(p, non_blocking=True)
+                jobs.append((self.end_points[offs[r]:offs[r + 1]], e[:n]))
+                jobs.append((self.support[offs[r]:offs[r + 1]], s_[:n]))
+            jobs.append((self._ptr2[r], p))
+        if copy_streams:
+            cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            order = sorted(range(len(jobs)), key=lambda k: -jobs[k][1].numel())     # big copies first, round-robin
+            for k, j in enumerate(order):
+                st = copy_streams[k % len(copy_streams)]
+                if k < len(copy_streams):
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    jobs[j][0].copy_(jobs[j][1], non_blocking=True)
+            for st in copy_streams[:len(jobs)]:
+                cur.wait_stream(st)
+        else:
+            for dst, src in jobs:
+                dst.copy_(src, non_blocking=True)
         self.cat_indptr[:R * n_dst].view(R, n_dst).copy_(self._ptr2[:, :n_dst] + self._offs_dev[:, None])
         return self
 
@@ -149,24 +168,9 @@ class MultiLinkCSR:
         self._t = None
         self._t_ws = None
         self._t_sched = None
-        self._reverse = None
-        self._not_found = None
+        self.keep_transpose_scratch = False   # True: keep the sort outputs (~8 B/edge) so refresh_weights_ is one launch
         self._ptr2 = None
         self.h2d_bytes = 4 * (2 * self.nnz + self.n_seg + 1)
-
-    def set_reverse(self, other):
-        """Declare ``other`` to be the plan of the REVERSE direction over the same edge set with the same edge
-        (both directions of a full-neighbourhood bipartite layer; end points ascending inside every segment, as
-        scipy's CSR and the reference's split deliver them).  The transposed operands of each plan are then read off
-        the other plan's CSR by two small kernels instead of a radix sort (sg_multilink_transpose_from_reverse;
-        bit-identical result on such a pair).  ``reverse_mismatches()`` tells afterwards whether the declaration held."""
-        if other is not None and not (other.R == self.R and other.nnz == self.nnz and other.n_dst == self.n_nb
-                                      and other.n_nb == self.n_dst):
-            raise ValueError("the reverse plan must have the transposed shape and the same number of edges")
-        self._reverse = other
-        self._t = None
-        self._t_sched = None
-        return self
 
     def to_lists(self):
         """The reference's per-level ``(end_points_l, indptr_l, support_l)`` lists as numpy arrays (inspection /
@@ -186,11 +190,6 @@ class MultiLinkCSR:
             self._sched = Schedule(self.cat_indptr, self.nnz, self.chunk)
         return self._sched
 
-    def reverse_mismatches(self):
-        """Number of reverse-plan edges this plan does not hold, as seen by the last sort-free transposed build
-        (0 for a true pair of transposes).  Synchronises."""
-        return 0 if self._not_found is None else int(self._not_found.item())
-
     def _build_transposed(self, out=None):
         """(t_indptr [n_nb+1], t_src [nnz] = i*R + r, t_w [nnz]); ``out`` = existing buffers to refill in place."""
         lib = _lib.load()
@@ -200,18 +199,6 @@ class MultiLinkCSR:
             out = (torch.empty(self.n_nb + 1, dtype=torch.int32, device=dev),
                    torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev))
         t_indptr, t_src, t_w = out
-        if self._reverse is not None:
-            rev = self._reverse
-            if self._t_ws is None:
-                self._t_ws = (_bytes(lib.sg_multilink_transpose_from_reverse_ws_bytes(self.n_nb), dev),)
-            if self._not_found is None:
-                self._not_found = torch.zeros(1, dtype=torch.int32, device=dev)
-            check(lib.sg_multilink_transpose_from_reverse(_p(t_indptr), _p(t_src), _p(t_w), _p(self._not_found),
-                                                          _p(rev.end_points), _p(rev.cat_indptr), _p(self.end_points),
-                                                          _p(self.cat_indptr), _p(self.support), self.R, self.n_dst,
-                                                          self.n_nb, self.nnz, _p(self._t_ws[0]), _stream()),
-                  "sg_multilink_transpose_from_reverse")
-            return out
         if self._t_ws is None:
             ws_bytes = lib.sg_csr_transpose_ws_bytes(self.n_seg, self.n_nb, self.nnz)
             if ws_bytes == 0:
@@ -229,15 +216,22 @@ class MultiLinkCSR:
         """(t_indptr [n_nb+1], t_src [nnz] = i*R + r, t_w [nnz]) built once per plan."""
         if self._t is None:
             self._t = self._build_transposed()
-            if self.nnz > (1 << 20):
-                self._t_ws = None if self._reverse is None else self._t_ws   # the sort scratch (~100 B/edge) is not kept
+            if self.nnz > (1 << 20) and not self.keep_transpose_scratch:
+                self._t_ws = None                   # the sort scratch (~30 B/edge) is not kept for big plans
         return self._t
 
     def refresh_weights_(self):
         """The edge weights (``support``) were rewritten in place, the pattern did not change: re-derive only what
-        depends on the weights — the transposed weight array.  CUDA-graph capturable."""
+        depends on the weights — the transposed weight array (one launch when the sort outputs were kept,
+        ``keep_transpose_scratch``; a full re-sort otherwise).  CUDA-graph capturable."""
         if self._t is not None:
-            self._build_transposed(self._t)
+            if self._t_ws is not None:
+                _ws, _n, t_perm, t_seg = self._t_ws
+                check(_lib.load().sg_multilink_transpose_finish(_p(self._t[1]), _p(self._t[2]), _p(t_perm), _p(t_seg),
+                                                                _p(self.support), self.R, self.n_dst, self.nnz, _stream()),
+                      "sg_multilink_transpose_finish")
+            else:
+                self._build_transposed(self._t)
         return self
 
     def rebuild_(self, backward=True):
@@ -345,10 +339,13 @@ def _split_tf32(src, ld_dst, transpose=False):
     return hi, lo
 
 
-# True: the large activation operands (agg, gZ, Dense inputs) go to the GEMM as plain fp32 and are split into
-# their TF32 hi/lo parts inside the kernel; False: a producer pass writes both halves to HBM first (round-1 path,
-# kept for A/B measurements and as the fallback for operands whose row stride is not a multiple of 4 floats).
-GEMM_INKERNEL_SPLIT = True
+# False (shipped): the producers of the large activation operands (the gather kernel for agg, the activation-gradient
+# kernel for gZ) write the TF32 hi / lo halves, the GEMM streams both.  True: the operands go to the GEMM as plain
+# fp32 and are split inside the kernel (tf32x3_gemm_split_kernel) — half the operand bytes in HBM and through TMA,
+# but measured SLOWER on the B200 (forward transform 0.167 vs 0.131 ms, weight gradient 0.200 vs 0.130 ms: the
+# splitter's stage hand-over sits in the MMA warp's critical path and the 192 KB operand ring cannot get deeper;
+# profiles/r02_summary.md).  Kept as a tested option (tests/test_gemm_gpu.py) and for A/B runs (bench.py --inkernel-split).
+GEMM_INKERNEL_SPLIT = False
 
 
 def _raw_ok(t):

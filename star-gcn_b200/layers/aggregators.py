@@ -59,7 +59,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
             self._units = self._units // num_links
         self.reference_order = reference_order
         self.grad_group = None     # torch.distributed group: all-reduce the weight gradient inside backward
-        self.tensor_cores = True   # False: fp32 cuBLAS transform after the fused gather (A/B comparison)
+        self.tensor_cores = True   # False: unfused path (generic gather kernel + Dense GEMM), kept for A/B runs
         self.dropout = nn.Dropout(dropout_rate)
         # parameters are named weight{i} / bias{i} as in the reference (aggregators.py:86-97)
         for i in range(num_links):
@@ -147,21 +147,26 @@ class MultiLinkGCNAggregator(BaseAggregator):
             raise ValueError(f"plan has {csr.R} links, aggregator was built for {self._num_links}")
         D = neighbor_data.shape[1]
         code = activation_code(self._act)
-        if (self._accum == "sum" or self._num_links == 1) and D in FUSED_DIMS and code is not None and self.tensor_cores:
-            # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
-            w_ext = pack_w_ext(ws, bs)                                # (U, R*D + R)
-            return fused_agg_transform(neighbor_data, w_ext, csr, {0: 1.0, 1: 0.1, 2: 0.0}[code], self.grad_group)
-        agg, wsum = multilink_aggregate(neighbor_data, csr)           # (n_dst, R*D), (n_dst, R)
+        # One packed operand for every accumulation mode: 'sum' lays the level weights side by side,
+        # w_ext = [W_0 | ... | W_{R-1} | b_0 ... b_{R-1}]  (U, R*D + R);  'stack' (aggregators.py:79-81,151-153 —
+        # shipped by cfg/inductive_ml_100k_item_*.yml) is the same GEMM with a BLOCK-DIAGONAL operand: row block r
+        # holds W_r in the columns of level r and b_r in bias column r, so out[:, r*U_r:(r+1)*U_r] = agg_r W_r^T +
+        # wsum_r b_r without a batched library GEMM (the zero blocks cost R x the flops of a layer that is tiny).
         if self._accum == "sum" or self._num_links == 1:
-            w_cat = torch.cat(ws, dim=1)                              # (U, R*D)
-            b_mat = torch.stack(bs, dim=0)                            # (R, U)
-            out = torch.addmm(wsum @ b_mat, agg, w_cat.t())
+            w_ext = pack_w_ext(ws, bs)
         else:
-            a3 = agg.view(csr.n_dst, csr.R, D).transpose(0, 1)        # (R, n_dst, D)
-            w3 = torch.stack(ws, dim=0).transpose(1, 2)               # (R, D, U_r)
-            o3 = torch.bmm(a3, w3) + wsum.t().unsqueeze(-1) * torch.stack(bs, dim=0).unsqueeze(1)
-            out = o3.transpose(0, 1).reshape(csr.n_dst, csr.R * self._units)
-        return self._act(out)
+            w_ext = torch.cat([torch.block_diag(*ws), torch.block_diag(*[b.unsqueeze(1) for b in bs])], dim=1)
+        slope = {0: 1.0, 1: 0.1, 2: 0.0}.get(code, 1.0)     # activations the epilogue cannot carry run afterwards
+        if D in FUSED_DIMS and self.tensor_cores:
+            # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
+            out = fused_agg_transform(neighbor_data, w_ext, csr, slope, self.grad_group)
+        else:
+            # any other width: the generic gather kernel, then the same tensor-core GEMM through the Dense path
+            from ..decoder import fused_dense
+            agg, wsum = multilink_aggregate(neighbor_data, csr)       # (n_dst, R*D), (n_dst, R)
+            out = fused_dense(torch.cat([agg, wsum], dim=1), w_ext, None,
+                              {1.0: None, 0.1: "leaky", 0.0: "relu"}[slope])
+        return out if code is not None else self._act(out)
 
     def _forward_reference_order(self, neighbor_data, end_points_l, indptr_l, support_l, ws, bs):
         if isinstance(end_points_l, MultiLinkCSR):

@@ -81,13 +81,9 @@ class StaticGraphStep:
         self.dev = dev
         u, i = self.user, self.item
         self.dirs = {(u, i): _Direction(graph[u, i]), (i, u): _Direction(graph[i, u])}
-        self.dirs[(u, i)].csr.set_reverse(self.dirs[(i, u)].csr)
-        self.dirs[(i, u)].csr.set_reverse(self.dirs[(u, i)].csr)
         for d in self.dirs.values():
+            d.csr.keep_transpose_scratch = True       # the weights change every iteration, the pattern never does
             d.csr.prepare(backward=True)
-        for d in self.dirs.values():
-            if d.csr.reverse_mismatches():
-                raise ValueError("the two directions of the graph are not each other's transpose")
         if not (torch.equal(graph[u, i].col_ids, graph[i, u].row_ids) and torch.equal(graph[i, u].col_ids, graph[u, i].row_ids)):
             raise ValueError("the columns of each direction must list the nodes in the order of the other direction's rows")
         self.all_ids = {u: graph[u, i].row_ids, i: graph[i, u].row_ids}
@@ -99,6 +95,9 @@ class StaticGraphStep:
         self.recon = {k: torch.zeros(int(n), dtype=torch.int32, device=dev) for k, n in n_recon.items()}
         self.loss = None
         self._graph = None
+        # the two node types are independent inside a block: their layers run as two branches (two streams eagerly,
+        # parallel branches of the captured graph) — these graphs are chains of tiny kernels, latency-bound
+        self._streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
     # ---- the captured body ----
     def _body(self):
@@ -119,17 +118,29 @@ class StaticGraphStep:
         gt = {k: decoder.get_embed(m.embed_layers[k].weight, ids, None, use_mask=False) for k, ids in self.recon.items()}
         recon_rows = {u: self.graph[u, i].rows_of(self.recon[u]).contiguous() if u in self.recon else None,
                       i: self.graph[i, u].rows_of(self.recon[i]).contiguous() if i in self.recon else None}
+        from .runtime import fork_join
         pred_ratings, pred_embeddings = [], []
         for b in range(m._n_blocks):
             layer = m.encoders[b][0]
-            h = {u: layer.forward_single(u, feats[u], {i: (feats[i], d_ui.csr, None, None, None)}),
-                 i: layer.forward_single(i, feats[i], {u: (feats[u], d_iu.csr, None, None, None)})}
-            pu = m.rating_user_projs[b](decoder.take_rows(h[u], rows_u))
-            pv = m.rating_item_projs[b](decoder.take_rows(h[i], rows_i))
-            pred_ratings.append(m.gen_ratings(pu, pv))
-            pred_embeddings.append({k: m.embed_maps[b][k](h[k], recon_rows[k]) for k in self.recon})
-            if b < m._n_blocks - 1:
-                feats = {k: m.embed_maps[b][k](h[k]) for k in (u, i)}
+            last = b == m._n_blocks - 1
+            h, proj, pe, nxt = {}, {}, {}, {}
+
+            def branch(k, other, d, rows):
+                h[k] = layer.forward_single(k, feats[k], {other: (feats[other], d.csr, None, None, None)})
+                head = m.rating_user_projs[b] if k == u else m.rating_item_projs[b]
+                proj[k] = head(decoder.take_rows(h[k], rows))
+                if k in self.recon:
+                    pe[k] = m.embed_maps[b][k](h[k], recon_rows[k])
+                if not last:
+                    nxt[k] = m.embed_maps[b][k](h[k])
+
+            with fork_join(self._streams) as run:
+                run(0, lambda: branch(u, i, d_ui, rows_u))
+                run(1, lambda: branch(i, u, d_iu, rows_i))
+            pred_ratings.append(m.gen_ratings(proj[u], proj[i]))
+            pred_embeddings.append({k: pe[k] for k in self.recon})
+            if not last:
+                feats = nxt
         loss = m.loss(pred_ratings, pred_embeddings, gt, self.ratings, self.mean, self.std, self.lam)
         loss.backward()
         self.loss = loss.detach()

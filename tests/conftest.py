@@ -15,12 +15,16 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", autouse=True)
 def _gemm_operand_path():
-    """SGTEST_PRESPLIT=1 runs the whole suite on the round-1 GEMM operand path (activations pre-split in HBM) —
-    a test-harness switch for A/B runs; the library itself reads no environment variables."""
-    if os.environ.get("SGTEST_PRESPLIT") == "1":
+    """SGTEST_INKERNEL_SPLIT=1 runs the whole suite with the GEMM operands split inside the kernel (the optional
+    path, see graph.GEMM_INKERNEL_SPLIT) — a test-harness switch; the library itself reads no environment variables."""
+    if os.environ.get("SGTEST_INKERNEL_SPLIT") == "1":
         import stargcn_b200  # noqa: F401
         from stargcn_b200 import graph
-        graph.GEMM_INKERNEL_SPLIT = False
+        graph.GEMM_INKERNEL_SPLIT = True
+    if os.environ.get("SGTEST_GEMM_CHAIN"):       # A/B: k-blocks per TMEM accumulation chain (accuracy vs speed)
+        import stargcn_b200  # noqa: F401
+        from stargcn_b200 import _lib
+        _lib.dev_option("gemm_chain", int(os.environ["SGTEST_GEMM_CHAIN"]))
     yield
 
 

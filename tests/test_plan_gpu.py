@@ -1,6 +1,5 @@
 """Device plan maintenance (stargcn_b200.graph.MultiLinkCSR): construction from per-level lists without host
-concatenation, the sort-free transposed operands of a mutually transposed pair (bit-exact against the radix-sort
-path), and the in-place refresh + rebuild used by same-shaped iterations (CUDA-graph capturable)."""
+concatenation, and the in-place refresh + rebuild used by same-shaped iterations (CUDA-graph capturable)."""
 import numpy as np
 import pytest
 import torch
@@ -44,32 +43,6 @@ def test_construction_from_numpy_pinned_and_device_lists_agree():
     bad[1][3] = wl["n_item"]
     with pytest.raises(ValueError):
         MultiLinkCSR(bad, ptr_l, sup_l, n_nb=wl["n_item"], device="cuda", validate=True)
-
-
-@pytest.mark.parametrize("shape", ["ml-100k", "ml-1m"])
-def test_transposed_operands_from_the_reverse_plan_are_bit_exact(shape):
-    wl = layer_lists(shape)
-    u_sort, i_sort = build(wl, "user"), build(wl, "item")
-    u_rev, i_rev = build(wl, "user"), build(wl, "item")
-    u_rev.set_reverse(i_rev)
-    i_rev.set_reverse(u_rev)
-    for a, b in ((u_sort, u_rev), (i_sort, i_rev)):
-        ta, tb = a.transposed(), b.transposed()
-        assert torch.equal(ta[0], tb[0]) and torch.equal(ta[1], tb[1])
-        # the weights are the plan's own (the two directions' supports differ in the last bit: (1/d_r)/d_c)
-        assert torch.equal(ta[2], tb[2])
-        assert b.reverse_mismatches() == 0
-    with pytest.raises(ValueError):
-        u_rev.set_reverse(u_sort)
-    # a pair that is NOT a pair of transposes is detected
-    from stargcn_b200.graph import MultiLinkCSR
-    ep_l, ptr_l, sup_l = wl["item"][:3]
-    ep_bad = [e.copy() for e in ep_l]
-    ep_bad[0][0] = (ep_bad[0][0] + 1) % wl["n_user"]
-    wrong = MultiLinkCSR(ep_bad, ptr_l, sup_l, n_nb=wl["n_user"], device="cuda")
-    u_chk = build(wl, "user").set_reverse(wrong)
-    u_chk.transposed()
-    assert u_chk.reverse_mismatches() > 0
 
 
 def test_refresh_in_place_and_graph_replay():

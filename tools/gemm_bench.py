@@ -1,8 +1,9 @@
 """Developer tool: the three GEMM shapes of the ML-10M user-side layer in isolation, per operand path.
     python tools/gemm_bench.py [reps]
-Prints ms per call (CUDA events, L2 flushed between repetitions) for: pre-split operands (round-1 path), raw A
-(split in the kernel), raw A and B; plus a check whether the tensor core TRUNCATES raw fp32 inputs to TF32 (then the
-raw tile itself can stand in for the 'hi' operand)."""
+Prints ms per call (CUDA events, L2 flushed between repetitions) for: pre-split operands (shipped path), raw A
+(split in the kernel), raw A and B; a check whether the tensor core TRUNCATES raw fp32 inputs to TF32 (then the
+raw tile itself can stand in for the 'hi' operand); and the TMA delivery rate per SM (sg_tma_probe) as a function of
+ring depth, boxes per barrier phase and the number of issuing warps.  Results of round 2: profiles/r02_summary.md."""
 import ctypes
 import os
 import sys
@@ -117,48 +118,6 @@ def main():
             by = 148 * iters * boxes * 16384
             print(f"tma probe {tag}, {prod} producer warp(s): {stages} stages x {boxes} boxes ({stages * boxes * 16} KB in flight): "
                   f"{by / ms / 1e6 / 148:.1f} GB/s per SM, {by / ms / 1e9:.2f} TB/s total")
-    # --- is the A operand's DRAM access pattern (128-byte pieces 2.6 KB apart) what starves the pipeline? ---
-    # (1) same GEMM with the rows of A that fit the L2 (warm, no flush): time per 256-row tile
-    for m_small in (8192, 16384):
-        o = torch.empty((m_small, U), device=dev)
-        fn = lambda: gemm(o, agg_hi[:m_small], agg_lo[:m_small], w_hi, w_lo, m_small, U, Kx)
-        for _ in range(5):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
-        print(f"fwd pre-split, M={m_small} (A L2-resident, warm): {ms:.4f} ms = {ms * 1e3 / (m_small / 256):.3f} us per 256-row tile "
-              f"(tiles per pair round: {m_small / 256 / 74:.2f})")
-    # (2) the full GEMM with A stored k-block-major [kb][rows][32] (every TMA box = 16 KB contiguous)
-    n_kb = (Kx + 31) // 32
-    blk_hi = agg_hi.view(n, n_kb, 32).permute(1, 0, 2).contiguous()
-    blk_lo = agg_lo.view(n, n_kb, 32).permute(1, 0, 2).contiguous()
-    out_blk = torch.empty_like(out)
-    _lib.dev_option("gemm_a_block_rows", n)
-    check(lib.sg_gemm_tf32x3(_p(out_blk), out_blk.stride(0), _p(blk_hi), _p(blk_lo), 32, _p(w_hi), _p(w_lo), w_hi.stride(0),
-                             n, U, Kx, 0, 0, ctypes.c_float(0.0), None, 1, None, _stream()), "gemm blk")
-    torch.cuda.synchronize()
-    print(f"k-block-major A: max|diff| vs row-major {float((out_blk - ref).abs().max()):.3e}")
-    t_blk = timeit(lambda: check(lib.sg_gemm_tf32x3(_p(out_blk), out_blk.stride(0), _p(blk_hi), _p(blk_lo), 32, _p(w_hi), _p(w_lo),
-                                                    w_hi.stride(0), n, U, Kx, 0, 0, ctypes.c_float(0.0), None, 1, None, _stream()), "g"),
-                   reps, flush)
-    _lib.dev_option("gemm_a_block_rows", 0)
-    print(f"fwd pre-split, A k-block-major: {t_blk:.4f} ms")
-    for exp in ():
-        _lib.dev_option("gemm_split_exp", exp)
-        t_a = timeit(lambda: gemm(out, agg_raw, None, w_hi, w_lo, n, U, Kx), reps, flush)
-        t_ab = timeit(lambda: gemm(gw, gz_raw, None, agg_raw, None, U, Kx, n, mn=True, splits=splits, ws=ws), reps, flush)
-        print(f"split experiment bits={exp} (1 relaxed arrive, 2 no proxy fence, 4 no split work, 8 cta-scope waits in the MMA thread): fwd raw A {t_a:.4f} ms, dW raw A+B {t_ab:.4f} ms")
-    _lib.dev_option("gemm_split_exp", 0)
-    _lib.dev_option("gemm_producers", 1)
-    for name, variants in cases.items():
-        v, fn = variants[0]
-        print(name + f":  single producer warp (round-1 kernel) {v}: {timeit(fn, reps, flush):.4f} ms")
-    _lib.dev_option("gemm_producers", 0)
     for name, variants in cases.items():
         print(name + ":  " + "   ".join(f"{v}: {timeit(fn, reps, flush):.4f} ms" for v, fn in variants))
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: new-kernel validation (own process + timeout each), GPU parity suite, default bench, A/B benches.
+# One gpurun call: GPU parity suite, smoke, default bench, A/B benches.
 # Usage (from the repo root, under gpurun):  bash tools/gpu_check.sh [quick|ncu]
 set -u
 mkdir -p gpurun_out
@@ -8,47 +8,33 @@ T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
 
-el "gemm tests first (a hang here must not take the suite with it)"
-timeout 300 python -m pytest tests/test_gemm_gpu.py -x -q > $O/pytest_gemm.log 2>&1
-GEMM_RC=$?
-echo "gemm pytest exit $GEMM_RC"; tail -5 $O/pytest_gemm.log
-PRE=""
-if [ $GEMM_RC -ne 0 ]; then PRE="SGTEST_PRESPLIT=1"; echo "!! in-kernel-split GEMM failed: running the suite on the pre-split path"; fi
-
 el "pytest -m gpu"
-env $PRE timeout 900 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q --tb=short > $O/pytest.log 2>&1
 echo "pytest exit $?" | tee -a $O/pytest.log
-tail -15 $O/pytest.log
+grep -vE "Warning|warn|^$|^  " $O/pytest.log | tail -15
 
 el "smoke"
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 
 el "bench default"
-BFLAG=""; if [ $GEMM_RC -ne 0 ]; then BFLAG="--presplit"; fi
-timeout 500 python bench.py $BFLAG > $O/bench_default.json 2> $O/bench_default.err
+timeout 500 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 echo "bench exit $?"; python tools/bench_summary.py < $O/bench_default.json; tail -3 $O/bench_default.err
 
 if [ "${1:-}" != "quick" ]; then
-  el "A/B: pre-split GEMM operands"
-  timeout 300 python bench.py --presplit --no-e2e --no-cpu-baseline > $O/bench_presplit.json 2> $O/bench_presplit.err
-  python tools/bench_summary.py < $O/bench_presplit.json
-  el "A/B: raw B operand off (K-major GEMMs take pre-split weights — default) vs staged gather"
-  timeout 300 python bench.py $BFLAG --no-e2e --no-cpu-baseline --dev gather_variant=1 > $O/bench_staged.json 2> $O/bench_staged.err
-  python tools/bench_summary.py < $O/bench_staged.json
+  el "A/B: GEMM operands split in the kernel"
+  timeout 300 python bench.py --inkernel-split --no-e2e --no-cpu-baseline > $O/bench_inkernel.json 2> $O/bench_inkernel.err
+  python tools/bench_summary.py < $O/bench_inkernel.json
   el "gather sweep: default vs staged (TMA bulk copy) variant"
   timeout 300 python tools/sweep_gather.py "gather_variant=0" "gather_variant=1" > $O/sweep_gather.log 2>&1; tail -6 $O/sweep_gather.log
-  el "A/B: release arrival"
-  timeout 300 python bench.py $BFLAG --no-e2e --no-cpu-baseline --dev gemm_arrive=1 > $O/bench_release.json 2> $O/bench_release.err
-  python tools/bench_summary.py < $O/bench_release.json
 fi
 if [ "${1:-}" == "ncu" ]; then
   el "ncu launch list (eager, 5 steps)"
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_eager.csv \
-      python bench.py $BFLAG --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/ncu_launches.log 2>&1
+      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
   el "ncu --set full, gather + gemm kernels of one step"
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:'gather_rows|tf32x3' -s 20 -c 10 -o $O/prof_step \
-      python bench.py $BFLAG --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/ncu_full.log 2>&1
+      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
 el "done"
