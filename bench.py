@@ -53,8 +53,6 @@ def parse_args():
                          "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")
     ap.add_argument("--inkernel-split", action="store_true",
                     help="A/B: GEMM operands as plain fp32, split into TF32 hi/lo inside the kernel (default: pre-split by their producers)")
-    ap.add_argument("--copy-streams", type=int, default=3,
-                    help="e2e: extra CUDA streams the per-level list copies of a step are spread over (0: all on one copy stream)")
     ap.add_argument("--dev", action="append", default=[], metavar="NAME=VALUE",
                     help="development option of the library (sg_dev_option), e.g. gather_variant=1")
     return ap.parse_args()
@@ -905,7 +903,6 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
     from stargcn_b200 import runtime
     from stargcn_b200.graph import MultiLinkCSR
     copy_stream = torch.cuda.Stream(device=dev)
-    extra_copy = [torch.cuda.Stream(device=dev) for _ in range(args.copy_streams)]
     main = torch.cuda.current_stream()
     slots = []
     for _ in range(2):
@@ -943,7 +940,7 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
 
     def upload(slot):
         for side, h in host.items():
-            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"], copy_streams=extra_copy or None)
+            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"])
             with torch.no_grad():
                 slot[side]["x"].copy_(h["x"], non_blocking=True)
 
@@ -977,13 +974,13 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
         counter[0] += 1
         k = i % 2
         main.wait_event(ready[k])
-        issue_upload((i + 1) % 2)                       # prefetch the next step's inputs
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(main)
-        graphs[k][0]()
+        graphs[k][0]()                                  # one launch: the device works while the host issues the next upload
         g1.record(main)
         done[k].record(main)
         comp_ev.append((g0, g1))
+        issue_upload((i + 1) % 2)                       # prefetch the next step's inputs
         return float(graphs[k][1]["total"].item())      # D2H read of the step's result
 
     steps = max(3, min(args.steps, 50))

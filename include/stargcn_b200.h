@@ -174,6 +174,12 @@ int sg_multilink_agg_fwd_split(float *agg_hi, float *agg_lo, int ld_agg, const f
 int sg_multilink_transpose_finish(int32_t *t_src, float *t_w, const int32_t *t_perm,
                                   const int32_t *t_seg, const float *support, int R, int n_dst, int nnz,
                                   sg_stream_t stream);
+/* Upload n arrays from PINNED host memory (device-accessible under unified addressing) into device buffers with
+ * one kernel launch instead of n DMA copies — the 3*R per-level lists of a small plan (the reference uploads each
+ * with its own nd.array call, layers.py:366-377).  dst_device / src_pinned_host / bytes are HOST arrays of n entries;
+ * every segment 4-byte aligned and a multiple of 4 bytes; zero-length segments are skipped. */
+int sg_upload_segments(void *const *dst_device, const void *const *src_pinned_host, const size_t *bytes, int n,
+                       sg_stream_t stream);
 int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, const float *t_w,
                          const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
                          int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,

@@ -73,6 +73,7 @@ SIGNATURES = {
     "sg_act_bwd_split": (_c_int, [_c_p, _c_p, _c_int, _c_p, _c_p, _c_int, _c_int, ctypes.c_float, _c_p]),
     "sg_gemm_trace_read": (_c_int, [_c_p]),
     "sg_tma_probe": (_c_int, [_c_p] + [_c_int] * 7 + [_c_p]),
+    "sg_upload_segments": (_c_int, [_c_p, _c_p, _c_p, _c_int, _c_p]),
     "sg_row_gather_probe": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, ctypes.c_uint, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),
 }

@@ -103,13 +103,18 @@ class MultiLinkCSR:
         self._init_device(ep_cat, sup_cat, cat_indptr, chunk, use_schedule)
         self._ptr2, self._offs_dev, self._offs = ptr2, offs_dev, offs
 
-    def load_lists_(self, end_points_l, indptr_l, support_l, copy_streams=None):
+    ZERO_COPY_MAX_BYTES = 16 << 20
+
+    def load_lists_(self, end_points_l, indptr_l, support_l, zero_copy=None):
         """Refresh the plan IN PLACE from new per-level lists with the SAME per-level edge counts (same-shaped plan
-        of the next iteration): every level is copied straight into its slice of the existing device arrays
-        (asynchronously from pinned memory) and the concatenated indptr is re-assembled on the device.  The derived
-        structures are stale afterwards — call :meth:`rebuild_` (CUDA-graph capturable) before the next use.
-        ``copy_streams``: optional list of extra CUDA streams; the 3*R copies are spread over them so that the
-        per-copy DMA set-up of one overlaps the transfer of another (they fork from and join the current stream)."""
+        of the next iteration): every level goes straight into its slice of the existing device arrays and the
+        concatenated indptr is re-assembled on the device.  The derived structures are stale afterwards — call
+        :meth:`rebuild_` (CUDA-graph capturable) before the next use.
+
+        Transport: asynchronous DMA copies from pinned memory (one per list), or — ``zero_copy`` — ONE kernel that
+        reads all 3*R pinned host arrays directly (``sg_upload_segments``).  ``zero_copy=None`` picks the kernel for
+        plans below ``ZERO_COPY_MAX_BYTES`` whose lists are all pinned CPU tensors: there the ~60 DMA set-ups, not
+        the bytes, are what an upload costs."""
         if getattr(self, "_ptr2", None) is None:
             raise ValueError("load_lists_ needs a plan that was built from per-level lists")
         R, n_dst, offs = self.R, self.n_dst, self._offs
@@ -126,19 +131,18 @@ class MultiLinkCSR:
                 jobs.append((self.end_points[offs[r]:offs[r + 1]], e[:n]))
                 jobs.append((self.support[offs[r]:offs[r + 1]], s_[:n]))
             jobs.append((self._ptr2[r], p))
-        if copy_streams:
-            cur = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            order = sorted(range(len(jobs)), key=lambda k: -jobs[k][1].numel())     # big copies first, round-robin
-            for k, j in enumerate(order):
-                st = copy_streams[k % len(copy_streams)]
-                if k < len(copy_streams):
-                    st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    jobs[j][0].copy_(jobs[j][1], non_blocking=True)
-            for st in copy_streams[:len(jobs)]:
-                cur.wait_stream(st)
+        pinned = all((not src.is_cuda) and src.is_pinned() and src.is_contiguous() for _, src in jobs)
+        if zero_copy is None:
+            zero_copy = pinned and sum(src.numel() * 4 for _, src in jobs) <= self.ZERO_COPY_MAX_BYTES
+        if zero_copy:
+            if not pinned:
+                raise ValueError("zero_copy needs contiguous pinned CPU tensors")
+            n = len(jobs)
+            dsts = (ctypes.c_void_p * n)(*[dst.data_ptr() for dst, _ in jobs])
+            srcs = (ctypes.c_void_p * n)(*[src.data_ptr() for _, src in jobs])
+            sizes = (ctypes.c_size_t * n)(*[src.numel() * 4 for _, src in jobs])
+            check(_lib.load().sg_upload_segments(dsts, srcs, sizes, n, _stream()), "sg_upload_segments")
+            self._keep_alive = [src for _, src in jobs]      # the kernel reads them asynchronously
         else:
             for dst, src in jobs:
                 dst.copy_(src, non_blocking=True)

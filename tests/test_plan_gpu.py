@@ -93,3 +93,12 @@ def test_refresh_in_place_and_graph_replay():
     assert torch.equal(holder["out"], want_b[0]) and torch.equal(x.grad, want_b[1]) and torch.equal(agg.weight1.grad, want_b[2])
     with pytest.raises(ValueError):
         csr.load_lists_(pin(ep_b)[:-1], pin(ptr_l)[:-1], pin(sup_b)[:-1])
+    # the two transports (one kernel reading the pinned arrays / one DMA copy per list) deliver the same arrays
+    a, b = build(wl, "user"), build(wl, "user")
+    a.load_lists_(pin(ep_b), pin(ptr_l), pin(sup_b), zero_copy=True)
+    b.load_lists_(pin(ep_b), pin(ptr_l), pin(sup_b), zero_copy=False)
+    torch.cuda.synchronize()
+    assert torch.equal(a.end_points, b.end_points) and torch.equal(a.support, b.support) and torch.equal(a.cat_indptr, b.cat_indptr)
+    assert torch.equal(a.end_points, fresh_b.end_points) and torch.equal(a.cat_indptr, fresh_b.cat_indptr)
+    with pytest.raises(ValueError):
+        a.load_lists_(ep_b, ptr_l, sup_b, zero_copy=True)          # pageable numpy arrays cannot be read by the kernel
