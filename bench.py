@@ -53,6 +53,9 @@ def parse_args():
                          "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")
     ap.add_argument("--inkernel-split", action="store_true",
                     help="A/B: GEMM operands as plain fp32, split into TF32 hi/lo inside the kernel (default: pre-split by their producers)")
+    ap.add_argument("--upload", default="auto", choices=["auto", "dma", "kernel"],
+                    help="e2e list transport: one DMA copy per list, one kernel reading the pinned lists (sg_upload_segments), "
+                         "or auto (kernel for plans below 16 MB)")
     ap.add_argument("--dev", action="append", default=[], metavar="NAME=VALUE",
                     help="development option of the library (sg_dev_option), e.g. gather_variant=1")
     return ap.parse_args()
@@ -940,7 +943,7 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
 
     def upload(slot):
         for side, h in host.items():
-            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"])
+            slot[side]["csr"].load_lists_(h["ep_l"], h["ptr_l"], h["sup_l"], zero_copy={"auto": None, "dma": False, "kernel": True}[args.upload])
             with torch.no_grad():
                 slot[side]["x"].copy_(h["x"], non_blocking=True)
 

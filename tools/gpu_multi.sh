@@ -8,13 +8,13 @@ mkdir -p gpurun_out
 O=gpurun_out
 T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 1000)) "$@"; }
+run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 1000)) "$@"; }
 for w in $WHAT; do
   case $w in
-    check)  el "check"; timeout 600 run bench.py --gpus $N --check 2> $O/check_n$N.err | tee $O/check_n$N.json | cut -c1-900 ;;
-    weak)   el "weak (auto exchange)"; timeout 900 run bench.py --gpus $N --no-cpu-baseline --steps 100 --warmup 10 2> $O/weak_n$N.err > $O/weak_n$N.json; python tools/bench_summary.py < $O/weak_n$N.json ;;
-    a2a)    el "weak, all-to-all forced"; timeout 900 run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode alltoall --steps 100 --warmup 10 2> $O/a2a_n$N.err > $O/a2a_n$N.json; python tools/bench_summary.py < $O/a2a_n$N.json ;;
-    strong) el "strong (ML-10M itself, nnz-balanced ranges)"; timeout 900 run bench.py --gpus $N --no-cpu-baseline --no-e2e --scaling strong --steps 100 --warmup 10 2> $O/strong_n$N.err > $O/strong_n$N.json; python tools/bench_summary.py < $O/strong_n$N.json ;;
+    check)  el "check"; run bench.py --gpus $N --check 2> $O/check_n$N.err | tee $O/check_n$N.json | cut -c1-900 ;;
+    weak)   el "weak (auto exchange)"; run bench.py --gpus $N --no-cpu-baseline --steps 100 --warmup 10 2> $O/weak_n$N.err > $O/weak_n$N.json; python tools/bench_summary.py < $O/weak_n$N.json ;;
+    a2a)    el "weak, all-to-all forced"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode alltoall --steps 100 --warmup 10 2> $O/a2a_n$N.err > $O/a2a_n$N.json; python tools/bench_summary.py < $O/a2a_n$N.json ;;
+    strong) el "strong (ML-10M itself, nnz-balanced ranges)"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --scaling strong --steps 100 --warmup 10 2> $O/strong_n$N.err > $O/strong_n$N.json; python tools/bench_summary.py < $O/strong_n$N.json ;;
   esac
 done
 el "done"; tail -2 $O/*_n$N.err 2>/dev/null | grep -v "^$" | tail -12
