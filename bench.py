@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank owns an ML-10M-shaped slice of an N-times larger graph (default); "
                          "strong = the ML-10M graph itself, node ranges balanced by nnz (SURVEY 8e)")
-    ap.add_argument("--halo-mode", default="auto", choices=["auto", "alltoall", "allgather"],
+    ap.add_argument("--halo-mode", default="auto", choices=["auto", "nccl", "alltoall", "allgather", "peer"],
                     help="N>1: force the halo exchange (auto picks all-gather / reduce-scatter when the halo is dense)")
     ap.add_argument("--check", action="store_true",
                     help="N>1: run the partitioned step over NCCL in both exchange modes (and on the strong partition) on a "
@@ -358,7 +358,7 @@ def run_check(args, rank, world, local_rank):
         return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
     report, ok = {}, True
-    for scaling, mode in (("weak", "alltoall"), ("weak", "allgather"), ("strong", "alltoall")):
+    for scaling, mode in (("weak", "alltoall"), ("weak", "allgather"), ("strong", "alltoall"), ("weak", "peer"), ("strong", "peer")):
         sides = partition_sides(base, rank, world, scaling)
         s = sides["user"]
         indptr, cols, vals, sup = s["csr"]
@@ -373,9 +373,23 @@ def run_check(args, rank, world, local_rank):
         lo, hi = int(s["nb_ranges"][rank]), int(s["nb_ranges"][rank + 1])
         x_local = torch.from_numpy(x_all[lo:hi]).to(dev).requires_grad_(True)
         agg = make_agg()
-        out = agg(sgd.halo_exchange(x_local, plan), csr)
-        out.backward(torch.from_numpy(gout_all[s["dst_lo"]:s["dst_lo"] + s["n_dst"]]).to(dev))
-        sgd.allreduce_grads(list(agg.parameters()))
+        gout = torch.from_numpy(gout_all[s["dst_lo"]:s["dst_lo"] + s["n_dst"]]).to(dev)
+        if plan.mode == "peer":
+            # this library's own exchange over NVLink peer memory, weight gradient summed inside the backward; run
+            # a forward-only pass and a first training step in front so the buffers are REUSED by the step compared
+            agg.grad_group = dist.group.WORLD
+            with torch.no_grad():
+                sgd.partitioned_aggregate(agg, x_local, plan, csr)
+            sgd.partitioned_aggregate(agg, x_local, plan, csr).backward(gout * 0.5)
+            x_local.grad = None
+            for p_ in agg.parameters():
+                p_.grad = None
+        out = sgd.partitioned_aggregate(agg, x_local, plan, csr)
+        out.backward(gout)
+        if plan.mode == "peer":
+            plan._transport.check()
+        else:
+            sgd.allreduce_grads(list(agg.parameters()))
         mine = dict(out=out.detach().cpu().numpy(), gx=x_local.grad.cpu().numpy(), gw=agg.weight2.grad.cpu().numpy(),
                     gb=agg.bias2.grad.cpu().numpy(), dst_lo=s["dst_lo"], nb_lo=lo, n_halo=plan.n_halo, mode=plan.mode,
                     csr=(indptr, cols, vals, sup))
@@ -454,6 +468,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     import stargcn_b200  # noqa: F401
     from stargcn_b200 import _lib, graph
+    from stargcn_b200 import dist as sgd
     from stargcn_b200.graph import MultiLinkCSR
     from stargcn_b200.layers import MultiLinkGCNAggregator
 
@@ -556,8 +571,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         s["x"].grad = None
         for p in s["agg"].parameters():
             p.grad = None
-        xin = s["x"] if s["plan"] is None else sgd.halo_exchange(s["x"], s["plan"])
-        s["out"] = s["agg"](xin, s["csr"])
+        s["out"] = sgd.partitioned_aggregate(s["agg"], s["x"], s["plan"], s["csr"])
 
     def side_backward(s):
         out = s.pop("out")
@@ -614,6 +628,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     barrier()
     launches = _lib.launch_count() if not graphed else launches_per_step * args.steps
     ms_total = e0.elapsed_time(e1)
+    for s_ in sides.values():          # a peer barrier that timed out invalidates the run: fail loudly
+        if s_["plan"] is not None and s_["plan"]._transport is not None:
+            s_["plan"]._transport.check()
     if graphed:
         # per-kernel CUDA events cannot be read inside graph replays: time the same kernels on the same buffers
         # in an eager pass right after the timed region (single stream order, so the events bracket one kernel)
@@ -725,12 +742,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     else:
         what = (f"each rank owns an {args.workload}-shaped slice of a {world}x larger graph" if args.scaling == "weak" else
                 f"the {args.workload} graph itself cut into {world} contiguous node ranges per side, balanced by nnz")
-        coll = {"allgather": "NCCL all-gather of the neighbour-row blocks fwd + reduce-scatter bwd (dense halo: every rank needs "
+        coll = {"peer": "this library's kernels over NVLink peer memory (symmetric buffers): all-gather = every rank stores its "
+                        "block of neighbour rows into every rank's table; reduce-scatter = the transposed gather stores each "
+                        "gradient row into its owner's staging slot + fixed-order local sum; one flag barrier each; no NCCL in the step",
+                "allgather": "NCCL all-gather of the neighbour-row blocks fwd + reduce-scatter bwd (dense halo: every rank needs "
                              "nearly every remote row)",
                 "alltoall": "NCCL all-to-all(v) of deduplicated halo rows fwd + its transpose bwd"}
         parallelism = (f"node-partitioned over {world} GPUs ({what}); per layer direction: " +
                        "; ".join(f"{side} side: {coll[m]}, rank-0 halo {halo_by_side[side]} rows x {D * 4} B" for side, m in modes.items()) +
-                       "; all-reduce of the packed weight gradient inside the backward")
+                       "; sum of the packed weight gradient over ranks inside the backward")
     result = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                   ms_per_step=ms_per_step, higher_is_better=True,
                   scaling=args.scaling if world > 1 else "weak", vs_baseline=None, dtype="f32",
@@ -771,9 +791,8 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
     partitioned), and a scalar read-back ends it.  No device->host transfer other than that scalar."""
     import torch
     from stargcn_b200 import runtime
+    from stargcn_b200 import dist as sgd
     from stargcn_b200.graph import MultiLinkCSR
-    if world > 1:
-        from stargcn_b200 import dist as sgd
     R, D = wl["R"], wl["D"]
     host = {}
     h2d = 0
@@ -842,8 +861,7 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
             x = x.requires_grad_(True)
             for p in s["agg"].parameters():
                 p.grad = None
-            xin = x if s["plan"] is None else sgd.halo_exchange(x, s["plan"])
-            out = s["agg"](xin, csr)
+            out = sgd.partitioned_aggregate(s["agg"], x, s["plan"], csr)
             loss = 0.5 * (out * out).mean()
             loss.backward()
             losses[side] = loss.detach()

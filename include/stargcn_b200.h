@@ -39,6 +39,7 @@ enum { SG_REQ_NULL = 0, SG_REQ_WRITE = 1, SG_REQ_ADD = 3 };      /* mxnet::OpReq
 enum { SG_POOL_SUM = 0, SG_POOL_MEAN = 1, SG_POOL_MAX = 2 };     /* SegReduceType, seg_op.h:20 */
 enum { SG_REDUCE_SUM = 0, SG_REDUCE_MAX = 2, SG_REDUCE_MIN = 3 };
 enum { SG_BCAST_ADD = 0, SG_BCAST_MUL = 1, SG_BCAST_TO = 2, SG_BCAST_SUB = 3, SG_BCAST_DIV = 4 };
+#define SG_MAX_PEERS 8 /* ranks of one NVSwitch box */
 enum { SG_ACT_IDENTITY = 0, SG_ACT_LEAKY = 1, SG_ACT_RELU = 2 }; /* common.py:32-57 */
 
 const char *sg_last_error(void);
@@ -184,6 +185,31 @@ int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, 
                          const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst, int n_nb,
                          int nnz, int D, int req, const void *t_plan, int plan_chunk, float *partial,
                          sg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e)  Node-partitioned aggregation over NVLink / NVSwitch peer memory (no reference counterpart: the reference is
+ * single-device, experiments/STAR-GCN.py:32).  Every rank has mapped every rank's exchange buffer (symmetric memory);
+ * the `*_host` arguments are HOST arrays of `world` (<= SG_MAX_PEERS) DEVICE pointers, entry q addressing rank q's memory.
+ *   sg_peer_push_rows   all-gather / all-reduce input: store src[n_floats] to dst[q] for every q (one read, world stores)
+ *   sg_peer_barrier     flags[q] = rank q's flag array (>= world words, zero-initialised); state = 2 device words
+ *                       {epoch, error}: release-store the next epoch into flags[q][rank] for all q, acquire-spin until
+ *                       flags[rank][q] reached it.  A wait longer than timeout_s sets state[1] = 1 + missing rank and
+ *                       returns.  CUDA-graph replayable (the epoch is device state)
+ *   sg_peer_reduce      out (=|+=) stage[0] + stage[1] + ... + stage[world-1] in rank order, slot q at
+ *                       stage + q * slot_stride_floats — the local half of the reduce-scatter / all-reduce
+ *   sg_multilink_agg_bwd_peer   sg_multilink_agg_bwd whose output row j (global neighbour id) is stored at
+ *                       stage[q] + (j - owner_lo[q]) * D for the owner q of j (owner_lo[q] <= j < owner_lo[q+1]):
+ *                       the reduce-scatter's transfer happens inside the transposed gather.  D in {16, 32, 64, 128}.
+ * ---------------------------------------------------------------------------------------- */
+int sg_peer_push_rows(float *const *dst_host, const float *src, long long n_floats, int world, sg_stream_t stream);
+int sg_peer_barrier(uint32_t *const *flags_host, uint32_t *state, int rank, int world, double timeout_s,
+                    sg_stream_t stream);
+int sg_peer_reduce(float *out, const float *stage, long long n_floats, long long slot_stride_floats, int world,
+                   int req, sg_stream_t stream);
+int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int world, const float *gagg,
+                              const float *t_w, const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst,
+                              int n_nb, int nnz, int D, const void *t_plan, int plan_chunk, float *partial,
+                              sg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * A1 (transform part)  fp32-accurate GEMM on tcgen05 tensor cores (3xTF32 split)

@@ -76,6 +76,10 @@ SIGNATURES = {
     "sg_upload_segments": (_c_int, [_c_p, _c_p, _c_p, _c_int, _c_p]),
     "sg_row_gather_probe": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, ctypes.c_uint, _c_p]),
     "sg_multilink_agg_bwd": (_c_int, [_c_p] * 5 + [_c_int] * 6 + [_c_p, _c_int, _c_p, _c_p]),
+    "sg_peer_push_rows": (_c_int, [_c_p, _c_p, ctypes.c_longlong, _c_int, _c_p]),
+    "sg_peer_barrier": (_c_int, [_c_p, _c_p, _c_int, _c_int, ctypes.c_double, _c_p]),
+    "sg_peer_reduce": (_c_int, [_c_p, _c_p, ctypes.c_longlong, ctypes.c_longlong, _c_int, _c_int, _c_p]),
+    "sg_multilink_agg_bwd_peer": (_c_int, [_c_p, _c_p, _c_int] + [_c_p] * 4 + [_c_int] * 5 + [_c_p, _c_int, _c_p, _c_p]),
 }
 
 _lib = None

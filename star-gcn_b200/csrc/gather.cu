@@ -92,6 +92,16 @@ __device__ __forceinline__ long long out_offset(const GatherArgs &a, int seg) {
   return (long long)i * a.ld_out + (long long)r * a.F;
 }
 
+// Destination of output row `row` when the rows are scattered to their owners' staging buffers (peer memory)
+__device__ __forceinline__ float *peer_row(const GatherArgs &a, int row) {
+  float *base = a.peer_out[0];
+  int lo = 0;
+#pragma unroll
+  for (int q = 1; q < SG_MAX_PEERS; ++q)
+    if (q < a.peer_world && row >= a.peer_lo[q]) { base = a.peer_out[q]; lo = a.peer_lo[q]; }
+  return base + (long long)(row - lo) * a.ld_out;
+}
+
 template <int VEC, int LPR, int NV, int UNROLL>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a) {
   const int lane = threadIdx.x & (LPR - 1);
@@ -217,7 +227,7 @@ __device__ __forceinline__ float edge_weight(const GatherArgs &a, const float *_
 // registers and issues the loads of a batch further ahead; with the 40-register build (6 resident blocks
 // instead of 4) the long-segment launches were 5 % slower, and a 32-register cap (64 resident warps) did not
 // help the short-segment launch either — none of them is occupancy-bound (profiles/r01_summary.md §H).
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN, bool PEER>
 __global__ void __launch_bounds__(256, 1) gather_rows_fast_kernel(const GatherArgs a) {
   constexpr int F = LPR * NV * 4;
   const int lane = threadIdx.x & (LPR - 1);
@@ -301,7 +311,9 @@ __global__ void __launch_bounds__(256, 1) gather_rows_fast_kernel(const GatherAr
     } else {
       int rel = 0, row = d.z;  // segment = rel * n_out_rows + row (relation-major concatenated CSRs)
       if (a.n_out_rows != a.n_seg) { rel = seg_rel(a, d.z); row = d.z - rel * a.n_out_rows; }
-      float *orow = out + ((long long)row * a.ld_out + rel * F);
+      float *orow;
+      if constexpr (PEER) orow = peer_row(a, row);   // PEER implies PLAIN and n_out_rows == n_seg
+      else orow = out + ((long long)row * a.ld_out + rel * F);
       float inv = 1.f;
       if constexpr (!PLAIN) inv = (a.mean && d.y > d.x) ? 1.f / (float)(d.y - d.x) : 1.f;
 #pragma unroll
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(256, 1) gather_rows_fast_kernel(const GatherAr
             r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
           }
         }
-        if (a.out_lo) {
+        if (!PEER && a.out_lo) {
           const float4 hi = make_float4(tf32_hi(r.x), tf32_hi(r.y), tf32_hi(r.z), tf32_hi(r.w));
           reinterpret_cast<float4 *>(orow)[v * LPR + lane] = hi;
           reinterpret_cast<float4 *>(a.out_lo + (orow - a.out))[v * LPR + lane] =
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(256) gather_rows_staged_kernel(const GatherArg
 }
 
 // Second pass: fixed-order sum of the partial rows of every split segment.
-template <int VEC, int LPR, int NV>
+template <int VEC, int LPR, int NV, bool PEER = false>
 __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs a) {
   const int lane = threadIdx.x & (LPR - 1);
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -509,7 +521,9 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
         }
       }
     }
-    float *orow = out + out_offset(a, d.x);
+    float *orow;
+    if constexpr (PEER) orow = peer_row(a, d.x);
+    else orow = out + out_offset(a, d.x);
     float inv = 1.f;
     if (a.mean) {
       const int len = __ldg(a.indptr + d.x + 1) - __ldg(a.indptr + d.x);
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const GatherArgs 
 #pragma unroll
           for (int e = 0; e < VEC; ++e) r[e] += o[e];
         }
-        if (a.out_lo) {
+        if (!PEER && a.out_lo) {
           float h[VEC], l[VEC];
 #pragma unroll
           for (int e = 0; e < VEC; ++e) { h[e] = tf32_hi(r[e]); l[e] = r[e] - h[e]; }
@@ -589,7 +603,7 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false>
+template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false, bool PEER = false>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
   constexpr int kThreads = 256;
   constexpr int groups_per_block = kThreads / LPR;
@@ -597,13 +611,13 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
   const long long cap = grid_cap();
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
-  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN><<<grid, kThreads, 0, st>>>(a);
+  gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN, PEER><<<grid, kThreads, 0, st>>>(a);
   SG_LAUNCHED("gather_rows_fast_kernel");
   if (a.hdr && n_long_cap > 0) {
     long long cb = ceil_div<long long>(n_long_cap, groups_per_block);
     if (cb > cap) cb = cap;
     dim3 cgrid((unsigned)cb, (unsigned)K, 1);
-    combine_partials_kernel<4, LPR, NV><<<cgrid, kThreads, 0, st>>>(a);
+    combine_partials_kernel<4, LPR, NV, PEER><<<cgrid, kThreads, 0, st>>>(a);
     SG_LAUNCHED("combine_partials_kernel");
   }
   return SG_OK;
@@ -611,6 +625,8 @@ static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_c
 
 template <int LPR, int NV, int UNROLL>
 static int dispatch_fast_mode(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
+  if (a.peer_world > 0)   // rows scattered to their owners over NVLink (checked by run_gather: weights w[p], plain write)
+    return launch_fast<LPR, NV, UNROLL, 1, false, true, true>(a, K, n_items_cap, n_long_cap, st);
   if (a.inv_len_indptr) return launch_fast<LPR, NV, UNROLL, 3, false>(a, K, n_items_cap, n_long_cap, st);
   if (!a.w) return launch_fast<LPR, NV, UNROLL, 0, false>(a, K, n_items_cap, n_long_cap, st);
   if (a.perm) return launch_fast<LPR, NV, UNROLL, 2, false>(a, K, n_items_cap, n_long_cap, st);
@@ -662,6 +678,15 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
     a.hdr = nullptr; a.items = nullptr; a.longs = nullptr; a.partial = nullptr; a.partial_wsum = nullptr;
   }
   if (n_seg == 0 || a.F == 0) return SG_OK;
+  if (a.peer_world > 0) {
+    SG_REQUIRE(a.peer_world <= SG_MAX_PEERS && K == 1 && a.n_out_rows == n_seg && a.w && !a.perm && !a.inv_len_indptr &&
+                   !a.wsum && !a.out_lo && !a.mean && a.req == SG_REQ_WRITE && a.ld_src == a.F && a.ld_out == a.F &&
+                   (a.F == 16 || a.F == 32 || a.F == 64 || a.F == 128) && aligned(a.src, 16),
+               "peer-scattered output needs the plain weighted fast path (F in 16/32/64/128, write, batch 1)");
+    for (int q = 0; q < a.peer_world; ++q)
+      SG_REQUIRE(a.peer_out[q] && aligned(a.peer_out[q], 16), "peer staging pointer %d null or unaligned", q);
+    a.out = a.peer_out[0];   // only inspected for alignment below
+  }
   const bool v4 = a.F % 4 == 0 && a.ld_src % 4 == 0 && a.ld_out % 4 == 0 && aligned(a.src, 16) && aligned(a.out, 16) &&
                   (!a.partial || aligned(a.partial, 16)) && a.src_batch_stride % 4 == 0 && a.out_batch_stride % 4 == 0 &&
                   a.partial_batch_stride % 4 == 0;

@@ -445,4 +445,29 @@ int sg_multilink_agg_bwd(float *gx, const float *gagg, const float *t_w, const i
   return run_gather(a, 1, n_nb, nnz, t_plan, (cudaStream_t)stream);
 }
 
+int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int world, const float *gagg,
+                              const float *t_w, const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst,
+                              int n_nb, int nnz, int D, const void *t_plan, int plan_chunk, float *partial,
+                              sg_stream_t stream) {
+  SG_REQUIRE(world >= 1 && world <= SG_MAX_PEERS, "sg_multilink_agg_bwd_peer: world must be 1..%d", SG_MAX_PEERS);
+  SG_REQUIRE(R > 0 && n_dst >= 0 && n_nb >= 0 && nnz >= 0 && D > 0, "sg_multilink_agg_bwd_peer: bad sizes");
+  SG_REQUIRE(stage_host && owner_lo_host && t_indptr && (nnz == 0 || (gagg && t_w && t_src)),
+             "sg_multilink_agg_bwd_peer: null pointer");
+  SG_REQUIRE(owner_lo_host[0] == 0 && owner_lo_host[world] == n_nb, "sg_multilink_agg_bwd_peer: ownership ranges must cover [0, n_nb)");
+  if (n_nb == 0) return SG_OK;
+  GatherArgs a;
+  a.out = nullptr; a.ld_out = D; a.n_out_rows = n_nb;
+  a.src = gagg; a.ld_src = D;
+  a.w = t_w; a.idx = t_src; a.indptr = t_indptr; a.F = D; a.req = SG_REQ_WRITE;
+  a.plan_chunk = plan_chunk; a.partial = partial;
+  a.peer_world = world;
+  for (int q = 0; q < world; ++q) {
+    SG_REQUIRE(owner_lo_host[q] <= owner_lo_host[q + 1], "sg_multilink_agg_bwd_peer: ownership ranges must ascend");
+    a.peer_lo[q] = owner_lo_host[q];
+    a.peer_out[q] = stage_host[q];
+  }
+  a.peer_lo[world] = owner_lo_host[world];
+  return run_gather(a, 1, n_nb, nnz, t_plan, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -18,6 +18,11 @@ SURVEY §2.2).  This module is the B200-native answer for one box of 8 GPUs (SUR
     its transpose to a reduce-scatter: ``HaloPlan(mode="auto")`` then uses those NVSwitch collectives
     directly, with no pack / unpack and the global ids as column ids
   * the small relation-weight gradients are all-reduced (inside the fused backward, or ``allreduce_grads``)
+  * ``mode="peer"`` (picked by ``"auto"`` for a dense halo when symmetric memory is available) replaces the NCCL
+    collectives of the dense case by this library's own kernels over NVLink peer memory (csrc/peer.cu,
+    ``PeerTransport``): all-gather = every rank stores its block into every rank's table, reduce-scatter = the
+    transposed gather stores each gradient row straight into its owner's staging slot (the transfer rides inside
+    the gather launch) + a local fixed-order sum, gradient all-reduce = push + the same sum, one flag barrier each
 
 Index bookkeeping (``HaloPlan``) is host-side numpy + one all-to-all of index lists per plan and
 runs under gloo on CPU tensors as well (tests/test_dist_cpu.py); the row traffic itself needs
@@ -85,10 +90,11 @@ class HaloPlan:
         owner = np.searchsorted(self.owner_ranges, cols, side="right") - 1
         if cols.size and (cols.min() < 0 or cols.max() >= self.owner_ranges[-1]):
             raise ValueError("column id outside the partitioned id space")
-        if mode not in ("auto", "alltoall", "allgather"):
-            raise ValueError("mode must be 'auto', 'alltoall' or 'allgather'")
+        if mode not in ("auto", "alltoall", "allgather", "peer", "nccl"):
+            raise ValueError("mode must be 'auto', 'nccl', 'alltoall', 'allgather' or 'peer'")
+        self._transport = None
         self.mode = self._choose_mode(mode, cols, owner, index_device, exchange_fn)
-        if self.mode == "allgather":
+        if self.mode in ("allgather", "peer"):
             # dense halo: every rank fetches (almost) every remote row, so the exchange is an all-gather of the
             # equal-sized blocks and its transpose a reduce-scatter (NVSwitch collectives, no pack / unpack);
             # the concatenated table is indexed by the global ids themselves
@@ -134,8 +140,11 @@ class HaloPlan:
                 raise ValueError(f"rank {q} requested a row this rank does not own")
 
     def _choose_mode(self, mode, cols, owner, index_device, exchange_fn):
-        """'allgather' needs equal blocks; 'auto' picks it when at least half of all remote rows are needed by
-        EVERY rank (decided collectively so that all ranks take the same path)."""
+        """'allgather' needs equal blocks, 'peer' (this library's kernels over NVLink peer memory) takes any
+        contiguous ranges; 'auto' picks the dense exchange when at least half of all remote rows are needed by
+        EVERY rank — 'peer' when the ranks are CUDA devices of one box and at most SG_MAX_PEERS, else 'allgather'
+        for equal blocks — and the deduplicated all-to-all otherwise.  'nccl' = 'auto' without the peer transport.
+        Decided collectively so that all ranks take the same path."""
         sizes = np.diff(self.owner_ranges)
         equal = bool(np.all(sizes == sizes[0]))
         if self.world == 1 or mode == "alltoall":
@@ -144,15 +153,26 @@ class HaloPlan:
             if not equal:
                 raise ValueError("allgather mode needs equal-sized ownership blocks")
             return "allgather"
+        if mode == "peer":
+            if self.world > MAX_PEERS:
+                raise ValueError(f"peer mode handles at most {MAX_PEERS} ranks (one NVSwitch box)")
+            return "peer"
         remote = owner != self.rank
         n_needed = np.unique(cols[remote]).size
         n_remote = int(self.owner_ranges[-1]) - self.n_local
-        want = int(equal and n_remote > 0 and n_needed >= 0.5 * n_remote)
-        if exchange_fn is not None or not dist.is_initialized():
-            return "allgather" if want else "alltoall"
-        flag = torch.tensor([want], dtype=torch.int32, device=torch.device(index_device))
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        return "allgather" if int(flag.item()) else "alltoall"
+        dense = int(n_remote > 0 and n_needed >= 0.5 * n_remote)
+        collective = exchange_fn is None and dist.is_initialized()
+        if collective:
+            flag = torch.tensor([dense], dtype=torch.int32, device=torch.device(index_device))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            dense = int(flag.item())
+        if not dense:
+            return "alltoall"
+        peer_ok = (mode == "auto" and collective and self.world <= MAX_PEERS and torch.device(index_device).type == "cuda"
+                   and dist.get_backend(self.group) == "nccl")
+        if peer_ok:
+            return "peer"
+        return "allgather" if equal else "alltoall"
 
     # ---- device-side state for the row exchange ----
     def to(self, device):
@@ -174,6 +194,142 @@ class HaloPlan:
     @property
     def halo_bytes_per_row_float(self):
         return 4 * self.n_halo
+
+    def peer_transport(self, D, grad_floats, device):
+        """The symmetric-memory buffers of this direction (mode 'peer'), created collectively on first use."""
+        t = self._transport
+        if t is None or t.D != D or t.grad_capacity < grad_floats:
+            t = self._transport = PeerTransport(self, D, grad_floats, device)
+        return t
+
+
+MAX_PEERS = 8          # SG_MAX_PEERS (include/stargcn_b200.h)
+
+
+class PeerTransport:
+    """Exchange buffers of ONE layer direction in symmetric memory: every rank maps every rank's buffer, so the
+    collectives of the dense-halo case are this library's own kernels over NVLink peer memory (csrc/peer.cu).
+
+    Layout of each rank's buffer (fp32 words): [64 flag words | x_ext [n_total, D] | g_stage [world, slot] |
+    w_stage [world, grad_capacity]] — rank p writes block p of every x_ext (forward), slot p of every g_stage /
+    w_stage (backward); the owner sums its slots in rank order.  One stream per direction; see peer.cu for why
+    single buffers suffice."""
+    FLAG_WORDS = 64
+
+    def __init__(self, plan, D, grad_floats, device, timeout_s=10.0):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib, self._ctypes = _lib, ctypes
+        self.plan, self.D, self.timeout_s = plan, int(D), float(timeout_s)
+        self.rank, self.world = plan.rank, plan.world
+        self.device = torch.device(device)
+        if self.world > MAX_PEERS:
+            raise ValueError(f"peer transport handles at most {MAX_PEERS} ranks")
+        W, rank = self.world, self.rank
+        lo = [int(v) for v in plan.owner_ranges]
+        self.n_total, self.n_local = lo[-1], lo[rank + 1] - lo[rank]
+
+        def al(n):
+            return (int(n) + 63) // 64 * 64
+
+        self.slot = al(max(b - a for a, b in zip(lo[:-1], lo[1:])) * self.D)
+        self.grad_capacity = al(grad_floats)
+        off, pos = {}, self.FLAG_WORDS
+        for name, n in (("x_ext", al(self.n_total * self.D)), ("g_stage", W * self.slot), ("w_stage", W * self.grad_capacity)):
+            off[name], pos = pos, pos + n
+        self.off = off
+        group = plan.group if plan.group is not None else dist.group.WORLD
+        self.buf = symm.empty(pos, dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        base = [int(b) for b in self.handle.buffer_ptrs]
+        if len(base) != W or base[rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected pointer table")
+        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)            # every rank's flag words are zero before anyone can arrive
+
+        def table(vals):
+            return (ctypes.c_void_p * W)(*vals)
+
+        self._flags = table(base)
+        self._x_dst = table([b + 4 * (off["x_ext"] + lo[rank] * self.D) for b in base])
+        self._g_dst = table([b + 4 * (off["g_stage"] + rank * self.slot) for b in base])
+        self._w_dst = table([b + 4 * (off["w_stage"] + rank * self.grad_capacity) for b in base])
+        self._owner_lo = (ctypes.c_int32 * (W + 1))(*lo)
+        self.x_ext = self.buf[off["x_ext"]:off["x_ext"] + self.n_total * self.D].view(self.n_total, self.D)
+        self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + W * self.slot]
+        self._w_stage = self.buf[off["w_stage"]:off["w_stage"] + W * self.grad_capacity]
+        self._open = False                   # a forward whose consumers no barrier has covered yet
+
+    def _stream(self):
+        return self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _ptr(self, t):
+        return self._ctypes.c_void_p(t.data_ptr())
+
+    def barrier(self):
+        lib = self._lib.load()
+        self._lib.check(lib.sg_peer_barrier(self._flags, self._ptr(self.state), self.rank, self.world,
+                                            self.timeout_s, self._stream()), "sg_peer_barrier")
+
+    def all_gather(self, x_local, will_backward):
+        """x_local [n_local, D] -> the [n_total, D] table of every rank (a view of the symmetric buffer, valid until
+        the next all_gather).  ``will_backward``: the backward's barrier will cover this table's readers; otherwise
+        the caller ends its forward with :meth:`release`."""
+        if x_local.shape != (self.n_local, self.D) or x_local.dtype != torch.float32 or not x_local.is_contiguous():
+            raise ValueError(f"x_local must be a contiguous float32 [{self.n_local}, {self.D}] tensor")
+        if self._open:                       # the previous forward never reached a covering barrier
+            self.barrier()
+        lib = self._lib.load()
+        self._lib.check(lib.sg_peer_push_rows(self._x_dst, self._ptr(x_local), self.n_local * self.D, self.world,
+                                              self._stream()), "sg_peer_push_rows")
+        self.barrier()
+        self._open = True
+        return self.x_ext
+
+    def release(self):
+        """Forward-only use: the readers of x_ext have been issued; no rank may overwrite it before all arrive here."""
+        self.barrier()
+        self._open = False
+
+    def push_grad(self, g_flat):
+        """Store this rank's packed weight gradient (flat, <= grad_capacity floats, padded to 4) into every rank's slot."""
+        n = (g_flat.numel() + 3) // 4 * 4
+        if n > self.grad_capacity or g_flat.untyped_storage().nbytes() - 4 * g_flat.storage_offset() < 4 * n:
+            raise ValueError("gradient buffer larger than the staging slot or not padded to 4 floats")
+        lib = self._lib.load()
+        self._lib.check(lib.sg_peer_push_rows(self._w_dst, self._ptr(g_flat), n, self.world, self._stream()),
+                        "sg_peer_push_rows")
+
+    def scatter_args(self):
+        """(stage pointer table, ownership ranges, world) for sg_multilink_agg_bwd_peer."""
+        return self._g_dst, self._owner_lo, self.world
+
+    def reduce_rows(self):
+        """Sum of the world staging slots of this rank's rows, in rank order -> [n_local, D]."""
+        out = torch.empty((self.n_local, self.D), dtype=torch.float32, device=self.device)
+        if self.n_local:
+            lib = self._lib.load()
+            n = self.n_local * self.D
+            self._lib.check(lib.sg_peer_reduce(self._ptr(out), self._ptr(self._g_stage), n, self.slot, self.world, 1,
+                                               self._stream()), "sg_peer_reduce")
+        return out
+
+    def reduce_grad(self, g_flat):
+        """g_flat <- sum over ranks of the pushed gradients (rank order: the same bits on every rank)."""
+        n = (g_flat.numel() + 3) // 4 * 4
+        lib = self._lib.load()
+        self._lib.check(lib.sg_peer_reduce(self._ptr(g_flat), self._ptr(self._w_stage), n, self.grad_capacity, self.world, 1,
+                                           self._stream()), "sg_peer_reduce")
+        return g_flat
+
+    def check(self):
+        """Raise if a barrier timed out (synchronises)."""
+        err = int(self.state[1].item())
+        if err:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {err - 1} (direction group of rank {self.rank})")
 
 
 def _a2a_rows(out, inp, out_splits, in_splits, group):
@@ -219,6 +375,9 @@ class _HaloExchange(torch.autograd.Function):
         if plan.mode == "allgather":
             _all_gather_rows(x_ext, x_local, plan.group)
             return x_ext
+        if plan.mode == "peer":
+            raise RuntimeError("mode 'peer' is driven by the fused aggregation (MultiLinkGCNAggregator.halo_plan), "
+                               "not by halo_exchange()")
         x_ext[:plan.n_local].copy_(x_local)
         if plan.world > 1:
             if d["send_cat"].numel():   # pack: one gather launch over the cached one-edge-per-slot pattern
@@ -254,6 +413,19 @@ def halo_exchange(x_local, plan):
     if x_local.shape[0] != plan.n_local:
         raise ValueError(f"x_local has {x_local.shape[0]} rows, the plan owns {plan.n_local}")
     return _HaloExchange.apply(x_local.contiguous(), plan)
+
+
+def partitioned_aggregate(agg, x_local, plan, *plan_lists):
+    """One partitioned layer direction: ``agg`` (a MultiLinkGCNAggregator) over the rank's own neighbour rows
+    ``x_local`` and its CSR (a MultiLinkCSR or the three per-level lists, column ids = ``plan.local_cols``).
+    Mode 'peer' runs the exchange inside the fused op (NVLink peer memory); the NCCL modes exchange first."""
+    if plan is None:
+        return agg(x_local, *plan_lists)
+    if plan.mode == "peer":
+        agg.halo_plan = plan
+        return agg(x_local, *plan_lists)
+    agg.halo_plan = None
+    return agg(halo_exchange(x_local, plan), *plan_lists)
 
 
 def allreduce_grads(params, group=None):
@@ -315,5 +487,5 @@ def partitioned_layer_inputs(base, rank, world):
     return out
 
 
-__all__ = ["HaloPlan", "halo_exchange", "allreduce_grads", "contiguous_ranges", "balanced_ranges",
+__all__ = ["HaloPlan", "PeerTransport", "halo_exchange", "partitioned_aggregate", "allreduce_grads", "contiguous_ranges", "balanced_ranges",
            "partitioned_layer_inputs", "edge_owner"]

@@ -389,12 +389,21 @@ class _FusedAggTransform(torch.autograd.Function):
     gather.  w_ext [U, R*D + R] = [W_0 | ... | W_{R-1} | b_0 ... b_{R-1}]."""
 
     @staticmethod
-    def forward(ctx, x, w_ext, csr, slope, grad_group=None):
+    def forward(ctx, x, w_ext, csr, slope, grad_group=None, halo=None):
         lib = _lib.load()
         ctx.grad_group = grad_group
+        U, Kx = w_ext.shape
+        ctx.peer = None
+        if halo is not None:
+            # node-partitioned run over NVLink peer memory (dist.PeerTransport): x holds this rank's OWN neighbour rows;
+            # every rank stores its block into every rank's table, one flag barrier, and the gather below reads the
+            # whole [n_total, D] table through the plan's global column ids
+            will_backward = any(ctx.needs_input_grad[:2])
+            ctx.peer = peer = halo.peer_transport(x.shape[1], U * Kx, x.device)
+            ctx.n_local = x.shape[0]
+            x = peer.all_gather(x, will_backward)
         n_nb, D = x.shape
         R, n_dst = csr.R, csr.n_dst
-        U, Kx = w_ext.shape
         assert Kx == R * D + R
         ld = (Kx + 31) // 32 * 32
         dev = x.device
@@ -420,6 +429,8 @@ class _FusedAggTransform(torch.autograd.Function):
         ctx.csr, ctx.slope, ctx.dims = csr, slope, (n_nb, D, R, n_dst, U, Kx, ld)
         ctx.raw = agg_lo is None
         ctx.save_for_backward(agg_hi, agg_lo, out, w_ext)
+        if ctx.peer is not None and not will_backward:
+            ctx.peer.release()          # forward-only: no backward barrier will cover the table's readers
         return out
 
     @staticmethod
@@ -436,9 +447,12 @@ class _FusedAggTransform(torch.autograd.Function):
         check(lib.sg_act_bwd_split(_p(gz_hi), _p(gz_lo), ldz, _p(gout), _p(out), n_dst, U, ctypes.c_float(slope),
                                    _stream()), "sg_act_bwd_split")
         gx = gw = None
+        peer = ctx.peer
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros((U, Kx), dtype=torch.float32, device=dev) if n_dst == 0 else \
-                torch.empty((U, Kx), dtype=torch.float32, device=dev)
+            n_gw = (U * Kx + 3) // 4 * 4      # flat, padded to 16 bytes: the peer transport moves float4
+            gw_flat = torch.zeros(n_gw, dtype=torch.float32, device=dev) if (n_dst == 0 or n_gw != U * Kx) else \
+                torch.empty(n_gw, dtype=torch.float32, device=dev)
+            gw = gw_flat[:U * Kx].view(U, Kx)
             if n_dst > 0:
                 tiles = ((U + 127) // 128) * ((Kx + 255) // 256)
                 kb = (n_dst + 31) // 32
@@ -446,7 +460,9 @@ class _FusedAggTransform(torch.autograd.Function):
                 e0 = _prof_begin()
                 _gemm_tf32x3(gw, gz_hi, gz_lo, agg_hi, agg_lo, U, Kx, n_dst, mn_major=True, splits=splits)
                 _prof_end("gemm_dw", e0, csr)
-            if ctx.grad_group is not None:
+            if peer is not None and ctx.grad_group is not None:
+                peer.push_grad(gw_flat)   # into every rank's slot; summed after the backward barrier below
+            elif ctx.grad_group is not None:
                 # partitioned run: sum the packed weight gradient over ranks here, ONE collective per layer
                 # direction, issued before the transposed gather so NCCL overlaps it
                 import torch.distributed as dist
@@ -457,7 +473,8 @@ class _FusedAggTransform(torch.autograd.Function):
                     dist.all_reduce(host, group=ctx.grad_group)
                     gw.copy_(host)
         if ctx.needs_input_grad[0]:
-            gx = torch.empty((n_nb, D), dtype=torch.float32, device=dev)
+            if peer is None:
+                gx = torch.empty((n_nb, D), dtype=torch.float32, device=dev)
             if n_dst > 0:
                 wt_hi, wt_lo = _split_tf32(w_ext[:, :R * D], ldz, transpose=True)       # [R*D, ldz]
                 gagg = torch.empty((n_dst, R * D), dtype=torch.float32, device=dev)
@@ -474,10 +491,25 @@ class _FusedAggTransform(torch.autograd.Function):
             else:
                 plan, chunk, pp = ctypes.c_void_p(0), 0, ctypes.c_void_p(0)
             e0 = _prof_begin()
-            check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, n_dst, n_nb, csr.nnz,
-                                           D, 1, plan, chunk, pp, _stream()), "sg_multilink_agg_bwd")
+            if peer is not None:
+                # reduce-scatter fused into its producer: every finished gradient row goes straight into the owner's
+                # staging slot of this rank (NVLink stores inside the gather launch)
+                stage, owner_lo, world = peer.scatter_args()
+                check(lib.sg_multilink_agg_bwd_peer(stage, owner_lo, world, _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R,
+                                                    n_dst, n_nb, csr.nnz, D, plan, chunk, pp, _stream()),
+                      "sg_multilink_agg_bwd_peer")
+            else:
+                check(lib.sg_multilink_agg_bwd(_p(gx), _p(gagg), _p(t_w), _p(t_src), _p(t_indptr), R, n_dst, n_nb, csr.nnz,
+                                               D, 1, plan, chunk, pp, _stream()), "sg_multilink_agg_bwd")
             _prof_end("agg_bwd", e0, csr)
-        return gx, gw, None, None, None
+        if peer is not None:
+            peer.barrier()                    # every rank's rows and gradient slots have landed
+            peer._open = False
+            if ctx.needs_input_grad[0]:
+                gx = peer.reduce_rows()       # [n_local, D]: the world slots summed in rank order
+            if gw is not None and ctx.grad_group is not None:
+                peer.reduce_grad(gw_flat)
+        return gx, gw, None, None, None, None
 
 
 class _PackWExt(torch.autograd.Function):
@@ -510,15 +542,24 @@ def pack_w_ext(ws, bs):
     return _PackWExt.apply(len(ws), *ws, *bs)
 
 
-def fused_agg_transform(x, w_ext, csr, slope, grad_group=None):
-    """act([agg | wsum] . w_ext^T) with act = leaky(slope) (slope 1.0 = identity, 0.0 = ReLU)."""
+def fused_agg_transform(x, w_ext, csr, slope, grad_group=None, halo=None):
+    """act([agg | wsum] . w_ext^T) with act = leaky(slope) (slope 1.0 = identity, 0.0 = ReLU).
+
+    ``halo``: a ``dist.HaloPlan`` of mode 'peer' — ``x`` then holds only this rank's OWN neighbour rows and the
+    exchange (all-gather forward, reduce-scatter of the data gradient and all-reduce of the weight gradient
+    backward) runs inside this op over NVLink peer memory."""
     if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
         raise TypeError("x must be a 2-D float32 CUDA tensor")
-    if x.shape[0] != csr.n_nb:
+    if halo is not None:
+        if halo.mode != "peer":
+            raise ValueError("halo must be a HaloPlan of mode 'peer' (other modes go through dist.halo_exchange)")
+        if x.shape[0] != halo.n_local or csr.n_nb != halo.n_ext:
+            raise ValueError(f"x must hold the rank's {halo.n_local} own rows and the plan index all {halo.n_ext} rows")
+    elif x.shape[0] != csr.n_nb:
         raise ValueError(f"x has {x.shape[0]} rows but the plan indexes {csr.n_nb} neighbour rows")
     if x.shape[1] not in FUSED_DIMS:
         raise ValueError(f"the fused path needs D in {FUSED_DIMS}")
-    return _FusedAggTransform.apply(x.contiguous(), w_ext, csr, float(slope), grad_group)
+    return _FusedAggTransform.apply(x.contiguous(), w_ext, csr, float(slope), grad_group, halo)
 
 
 def multilink_aggregate(x, csr):

@@ -59,6 +59,8 @@ class MultiLinkGCNAggregator(BaseAggregator):
             self._units = self._units // num_links
         self.reference_order = reference_order
         self.grad_group = None     # torch.distributed group: all-reduce the weight gradient inside backward
+        self.halo_plan = None      # dist.HaloPlan of mode 'peer': neighbor_data holds the rank's OWN rows and the
+                                   # exchange runs inside the fused op over NVLink peer memory
         self.tensor_cores = True   # False: unfused path (generic gather kernel + Dense GEMM), kept for A/B runs
         self.dropout = nn.Dropout(dropout_rate)
         # parameters are named weight{i} / bias{i} as in the reference (aggregators.py:86-97)
@@ -142,7 +144,8 @@ class MultiLinkGCNAggregator(BaseAggregator):
         ws, bs = self._effective_params()
         if self.reference_order:
             return self._act(self._forward_reference_order(neighbor_data, end_points_l, indptr_l, support_l, ws, bs))
-        csr = self._plan(neighbor_data.shape[0], end_points_l, indptr_l, support_l)
+        n_rows = neighbor_data.shape[0] if self.halo_plan is None else self.halo_plan.n_ext
+        csr = self._plan(n_rows, end_points_l, indptr_l, support_l)
         if csr.R != self._num_links:
             raise ValueError(f"plan has {csr.R} links, aggregator was built for {self._num_links}")
         D = neighbor_data.shape[1]
@@ -159,7 +162,7 @@ class MultiLinkGCNAggregator(BaseAggregator):
         slope = {0: 1.0, 1: 0.1, 2: 0.0}.get(code, 1.0)     # activations the epilogue cannot carry run afterwards
         if D in FUSED_DIMS and self.tensor_cores:
             # gather (1 launch) + tcgen05 3xTF32 GEMM with the activation in its epilogue
-            out = fused_agg_transform(neighbor_data, w_ext, csr, slope, self.grad_group)
+            out = fused_agg_transform(neighbor_data, w_ext, csr, slope, self.grad_group, self.halo_plan)
         else:
             # any other width: the generic gather kernel, then the same tensor-core GEMM through the Dense path
             from ..decoder import fused_dense

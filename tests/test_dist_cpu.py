@@ -42,6 +42,10 @@ def _worker(rank, world, port, q):
             # dense halo -> the collectively chosen mode is the all-gather one: global ids index the gathered table
             auto = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="auto")
             ok_auto = auto.mode == "allgather" and auto.n_ext == xg.shape[0] and np.array_equal(auto.local_cols, cols)
+            # the peer-memory mode keeps global ids as well (any contiguous ranges; the kernels need CUDA, the plan does not)
+            peer = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="peer")
+            ok_auto = (ok_auto and peer.mode == "peer" and peer.n_ext == xg.shape[0] and np.array_equal(peer.local_cols, cols)
+                       and peer.n_local == ranges[rank + 1] - ranges[rank])
             lo, hi = ranges[rank], ranges[rank + 1]
             x_local = torch.from_numpy(xg[lo:hi])
             # row exchange emulated with a gloo all-to-all on CPU tensors (test stand-in for pack kernel + NCCL)

@@ -129,7 +129,9 @@ def test_partitioned_layer_matches_whole_graph(mode):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the NCCL transport needs two GPUs (run by `gpurun --gpus 2`)")
 def test_partitioned_step_over_nccl_matches_whole_graph():
     """`bench.py --check` under torchrun: the partitioned step over NCCL (all-to-all and all-gather / reduce-scatter
-    exchange on the weak construction, all-to-all on the nnz-balanced strong partition) against the whole graph."""
+    exchange on the weak construction, all-to-all on the nnz-balanced strong partition) and over this library's own
+    NVLink peer-memory kernels (csrc/peer.cu; equal and nnz-balanced ranges, buffers reused across a forward-only pass
+    and two training steps) against the whole graph."""
     import json
     import subprocess
     import sys
@@ -141,6 +143,6 @@ def test_partitioned_step_over_nccl_matches_whole_graph():
                        capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert line["ok"] and set(line["cases"]) == {"weak/alltoall", "weak/allgather", "strong/alltoall"}
+    assert line["ok"] and set(line["cases"]) == {"weak/alltoall", "weak/allgather", "strong/alltoall", "weak/peer", "strong/peer"}
     for case in line["cases"].values():
         assert case["ok"] and max(case["out"], case["gx"], case["gw"], case["gb"]) <= 1e-5

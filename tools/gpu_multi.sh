@@ -11,6 +11,9 @@ el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 1000)) "$@"; }
 for w in $WHAT; do
   case $w in
+    peertest) el "peer kernels on one device"; timeout 600 python -m pytest tests/test_peer_gpu.py -q -x 2>&1 | tail -4 ;;
+    nccl)   el "weak, NCCL collectives (all-gather / reduce-scatter)"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode nccl --steps 100 --warmup 10 2> $O/nccl_n$N.err > $O/nccl_n$N.json; python tools/bench_summary.py < $O/nccl_n$N.json ;;
+    strongnccl) el "strong, NCCL all-to-all"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --scaling strong --halo-mode nccl --steps 100 --warmup 10 2> $O/strongnccl_n$N.err > $O/strongnccl_n$N.json; python tools/bench_summary.py < $O/strongnccl_n$N.json ;;
     check)  el "check"; run bench.py --gpus $N --check 2> $O/check_n$N.err | tee $O/check_n$N.json | cut -c1-900 ;;
     weak)   el "weak (auto exchange)"; run bench.py --gpus $N --no-cpu-baseline --steps 100 --warmup 10 2> $O/weak_n$N.err > $O/weak_n$N.json; python tools/bench_summary.py < $O/weak_n$N.json ;;
     a2a)    el "weak, all-to-all forced"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode alltoall --steps 100 --warmup 10 2> $O/a2a_n$N.err > $O/a2a_n$N.json; python tools/bench_summary.py < $O/a2a_n$N.json ;;
