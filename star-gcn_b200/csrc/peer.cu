@@ -66,7 +66,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags flags, uint32_t *state, int rank, int world,
                                                           unsigned long long timeout_ns) {
   const uint32_t epoch = state[0] + 1;   // every lane reads the same word before lane 0 rewrites it below
+  const uint32_t failed = state[1];
   __syncwarp();
+  if (failed) return;                    // a barrier of this exchange already timed out: do not wait again
   const int q = threadIdx.x;
   if (q < world) {
     uint32_t *theirs = nullptr, *mine = nullptr;
