@@ -48,6 +48,8 @@ def parse_args():
                          "strong = the ML-10M graph itself, node ranges balanced by nnz (SURVEY 8e)")
     ap.add_argument("--halo-mode", default="auto", choices=["auto", "nccl", "alltoall", "allgather", "peer"],
                     help="N>1: force the halo exchange (auto picks all-gather / reduce-scatter when the halo is dense)")
+    ap.add_argument("--peer-push", default="auto", choices=["auto", "sm", "ce"],
+                    help="all-gather of the peer transport: store kernel (sm), copy-engine copies (ce), or ce for blocks >= 4 MB (auto)")
     ap.add_argument("--check", action="store_true",
                     help="N>1: run the partitioned step over NCCL in both exchange modes (and on the strong partition) on a "
                          "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")
@@ -368,6 +370,8 @@ def run_check(args, rank, world, local_rank):
         x_all = rs.normal(size=(n_nb_total, D)).astype(np.float32)
         gout_all = rs.normal(size=(n_dst_total, U)).astype(np.float32)
         plan = sgd.HaloPlan(cols, s["nb_ranges"], rank, world, index_device=dev, mode=mode).to(dev)
+        # the all-gather of the peer transport by the store kernel on the weak case, by copy-engine copies on the strong one
+        sgd.PEER_COPY_ENGINE_BYTES = 0 if (mode, scaling) == ("peer", "strong") else None
         lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, base["levels"])[:3]
         csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev)
         lo, hi = int(s["nb_ranges"][rank]), int(s["nb_ranges"][rank + 1])
@@ -476,6 +480,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if args.inkernel_split:
         graph.GEMM_INKERNEL_SPLIT = True
+    sgd.PEER_COPY_ENGINE_BYTES = {"auto": sgd.PEER_COPY_ENGINE_BYTES, "sm": None, "ce": 0}[args.peer_push]
     for kv in args.dev:
         name, _, val = kv.partition("=")
         _lib.dev_option(name, int(val))
@@ -660,7 +665,13 @@ def run_gpu_arm(args, rank, world, local_rank):
         pass
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     detail, gemm, tot_bytes, tot_ms = {}, {}, 0.0, 0.0
+    exchange = {}
     for tag, a, b, csr in prof:
+        if tag.startswith("peer"):       # exchange kernels of the peer transport; the last field is the HaloPlan
+            key = f"{tag}:{'user' if csr is sides['user']['plan'] else 'item'}"
+            d = exchange.setdefault(key, dict(ms=0.0, n=0))
+            d["ms"] += a.elapsed_time(b); d["n"] += 1
+            continue
         key = f"{tag}:{'user' if csr is sides['user']['csr'] else 'item'}"
         if tag.startswith("gemm"):
             Kx = R * D + R
@@ -771,6 +782,14 @@ def run_gpu_arm(args, rank, world, local_rank):
         result["scaling_note"] = "single GPU: the N=1 point of the weak-scaling series (per-GPU work is what every rank gets at N>1)"
     else:
         result["collective"] = dict(mode=modes, halo_rows_rank0=halo_by_side)
+        if exchange:
+            n_prof = max(min(args.steps, 20), 1)
+            result["collective"]["exchange_ms_per_step_rank0"] = {k: round(v["ms"] / n_prof, 5) for k, v in sorted(exchange.items())}
+            result["collective"]["exchange_note"] = ("CUDA events around the exchange launches in the eager single-stream pass after the "
+                                                     "timed region: peer_push = all-gather stores / copies, peer_barrier = flag barrier "
+                                                     "including the wait for the slowest rank, peer_reduce = local sum of the staging slots")
+            result["collective"]["all_gather_push"] = ("copy engines for blocks >= %d bytes, store kernel below" % sgd.PEER_COPY_ENGINE_BYTES
+                                                       if sgd.PEER_COPY_ENGINE_BYTES is not None else "store kernel (sg_peer_push_rows)")
     if transform is not None:
         result["transform_gemm"] = transform
     if sampler_info is not None:

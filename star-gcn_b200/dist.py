@@ -205,6 +205,11 @@ class HaloPlan:
 
 MAX_PEERS = 8          # SG_MAX_PEERS (include/stargcn_b200.h)
 
+# All-gather blocks of at least this many bytes go to the peers by the COPY ENGINES (one asynchronous device-to-device
+# copy per peer into its mapped table) instead of the SM store kernel: the bulk transfer then takes no SM while the
+# other layer direction's gather runs.  None: always the store kernel.  (bench.py --peer-push sm|ce)
+PEER_COPY_ENGINE_BYTES = 4 << 20
+
 
 class PeerTransport:
     """Exchange buffers of ONE layer direction in symmetric memory: every rank maps every rank's buffer, so the
@@ -262,6 +267,15 @@ class PeerTransport:
         self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + W * self.slot]
         self._w_stage = self.buf[off["w_stage"]:off["w_stage"] + W * self.grad_capacity]
         self._open = False                   # a forward whose consumers no barrier has covered yet
+        # this rank's block inside every rank's table, as tensors (copy-engine path of all_gather)
+        self._x_peer = [self.handle.get_buffer(q, (self.n_local, self.D), torch.float32, off["x_ext"] + lo[rank] * self.D)
+                        for q in range(W)]
+
+    def _prof(self, tag, fn):
+        from . import graph
+        e0 = graph._prof_begin()
+        fn()
+        graph._prof_end(tag, e0, self.plan)
 
     def _stream(self):
         return self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -271,8 +285,9 @@ class PeerTransport:
 
     def barrier(self):
         lib = self._lib.load()
-        self._lib.check(lib.sg_peer_barrier(self._flags, self._ptr(self.state), self.rank, self.world,
-                                            self.timeout_s, self._stream()), "sg_peer_barrier")
+        self._prof("peer_barrier", lambda: self._lib.check(
+            lib.sg_peer_barrier(self._flags, self._ptr(self.state), self.rank, self.world, self.timeout_s, self._stream()),
+            "sg_peer_barrier"))
 
     def all_gather(self, x_local, will_backward):
         """x_local [n_local, D] -> the [n_total, D] table of every rank (a view of the symmetric buffer, valid until
@@ -283,8 +298,15 @@ class PeerTransport:
         if self._open:                       # the previous forward never reached a covering barrier
             self.barrier()
         lib = self._lib.load()
-        self._lib.check(lib.sg_peer_push_rows(self._x_dst, self._ptr(x_local), self.n_local * self.D, self.world,
-                                              self._stream()), "sg_peer_push_rows")
+
+        def push():
+            if PEER_COPY_ENGINE_BYTES is not None and 4 * self.n_local * self.D >= PEER_COPY_ENGINE_BYTES:
+                for k in range(self.world):          # start with the next rank so that the links are used evenly
+                    self._x_peer[(self.rank + 1 + k) % self.world].copy_(x_local, non_blocking=True)
+            else:
+                self._lib.check(lib.sg_peer_push_rows(self._x_dst, self._ptr(x_local), self.n_local * self.D, self.world,
+                                                      self._stream()), "sg_peer_push_rows")
+        self._prof("peer_push", push)
         self.barrier()
         self._open = True
         return self.x_ext
@@ -313,8 +335,9 @@ class PeerTransport:
         if self.n_local:
             lib = self._lib.load()
             n = self.n_local * self.D
-            self._lib.check(lib.sg_peer_reduce(self._ptr(out), self._ptr(self._g_stage), n, self.slot, self.world, 1,
-                                               self._stream()), "sg_peer_reduce")
+            self._prof("peer_reduce", lambda: self._lib.check(
+                lib.sg_peer_reduce(self._ptr(out), self._ptr(self._g_stage), n, self.slot, self.world, 1, self._stream()),
+                "sg_peer_reduce"))
         return out
 
     def reduce_grad(self, g_flat):
