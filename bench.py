@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--halo-mode", default="auto", choices=["auto", "nccl", "alltoall", "allgather", "peer"],
                     help="N>1: force the halo exchange (auto picks all-gather / reduce-scatter when the halo is dense)")
     ap.add_argument("--peer-push", default="auto", choices=["auto", "sm", "ce"],
-                    help="all-gather of the peer transport: store kernel (sm), copy-engine copies (ce), or ce for blocks >= 4 MB (auto)")
+                    help="all-gather of the peer transport: the library default (auto = store kernel), store kernel (sm), copy-engine copies (ce)")
     ap.add_argument("--check", action="store_true",
                     help="N>1: run the partitioned step over NCCL in both exchange modes (and on the strong partition) on a "
                          "small graph and compare with the whole-graph result on rank 0; prints one JSON line, exit 1 on mismatch")

@@ -205,10 +205,12 @@ class HaloPlan:
 
 MAX_PEERS = 8          # SG_MAX_PEERS (include/stargcn_b200.h)
 
-# All-gather blocks of at least this many bytes go to the peers by the COPY ENGINES (one asynchronous device-to-device
-# copy per peer into its mapped table) instead of the SM store kernel: the bulk transfer then takes no SM while the
-# other layer direction's gather runs.  None: always the store kernel.  (bench.py --peer-push sm|ce)
-PEER_COPY_ENGINE_BYTES = 4 << 20
+# None (shipped): the all-gather is the store kernel (sg_peer_push_rows).  A byte count: blocks of at least that size go
+# to the peers by the COPY ENGINES instead (one asynchronous device-to-device copy per peer into its mapped table; no SM
+# is used).  Measured on 8 B200s (weak scaling, 17.9 MB block to 8 tables): store kernel 0.205 ms / step 1.870 ms, copy
+# engines 0.235 ms / step 1.954 ms — seven serial copies do not fill the NVLink ports the way 296 storing CTAs do
+# (profiles/r02_summary.md §G); at 2 GPUs both give 1.46 ms.  Kept as a tested option (bench.py --peer-push ce).
+PEER_COPY_ENGINE_BYTES = None
 
 
 class PeerTransport:
