@@ -603,12 +603,20 @@ static int dispatch_lpr(const GatherArgs &a, int K, int n_items_cap, int n_long_
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+// Threads per block of the fast gather launches.  Small blocks: (1) work items differ in length, so a block's slot
+// is held until its slowest lane group is done — 64-thread blocks waste less of it (sum of the four ML-10M launches
+// 0.790 ms at 256 threads, 0.757 at 128, 0.748 at 64; tools/sweep_gather.py); (2) a 64-thread block needs 3 - 4 K
+// registers and fits next to a resident GEMM CTA (53.7 K of the SM's 64 K), so the other direction's gather makes
+// progress while a transform runs instead of waiting for the SM to drain.
+constexpr int kFastGatherThreads = 64;
+
 template <int LPR, int NV, int UNROLL, int WMODE, bool WSUM, bool PLAIN = false, bool PEER = false>
 static int launch_fast(const GatherArgs &a, int K, int n_items_cap, int n_long_cap, cudaStream_t st) {
-  constexpr int kThreads = 256;
-  constexpr int groups_per_block = kThreads / LPR;
+  const int dv = dev_option(SG_DEV_GATHER_THREADS);
+  const int kThreads = dv == 64 || dv == 128 || dv == 256 ? dv : kFastGatherThreads;
+  const int groups_per_block = kThreads / LPR;
   long long blocks = ceil_div<long long>(n_items_cap > 0 ? n_items_cap : 1, groups_per_block);
-  const long long cap = grid_cap();
+  const long long cap = grid_cap() * (256 / kThreads);   // the same number of lane groups per SM whatever the block size
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)K, 1);
   gather_rows_fast_kernel<LPR, NV, UNROLL, WMODE, WSUM, PLAIN, PEER><<<grid, kThreads, 0, st>>>(a);

@@ -18,7 +18,7 @@ from stargcn_b200._lib import check  # noqa: E402
 from stargcn_b200.graph import MultiLinkCSR  # noqa: E402
 from stargcn_b200.seg_op import _p, _stream  # noqa: E402
 
-KNOBS = ("gather_variant", "gather_grid")
+KNOBS = ("gather_variant", "gather_grid", "gather_threads")
 
 
 def main():
