@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank owns an ML-10M-shaped slice of an N-times larger graph (default); "
                          "strong = the ML-10M graph itself, node ranges balanced by nnz (SURVEY 8e)")
-    ap.add_argument("--halo-mode", default="auto", choices=["auto", "nccl", "alltoall", "allgather", "peer"],
+    ap.add_argument("--halo-mode", default="auto", choices=["auto", "nccl", "alltoall", "allgather", "peer", "peer_dense", "peer_sparse"],
                     help="N>1: force the halo exchange (auto picks all-gather / reduce-scatter when the halo is dense)")
     ap.add_argument("--peer-push", default="auto", choices=["auto", "sm", "ce"],
                     help="all-gather of the peer transport: the library default (auto = store kernel), store kernel (sm), copy-engine copies (ce)")
@@ -360,7 +360,8 @@ def run_check(args, rank, world, local_rank):
         return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
     report, ok = {}, True
-    for scaling, mode in (("weak", "alltoall"), ("weak", "allgather"), ("strong", "alltoall"), ("weak", "peer"), ("strong", "peer")):
+    for scaling, mode in (("weak", "alltoall"), ("weak", "allgather"), ("strong", "alltoall"), ("weak", "peer"), ("strong", "peer"),
+                          ("weak", "peer_sparse"), ("strong", "peer_sparse")):
         sides = partition_sides(base, rank, world, scaling)
         s = sides["user"]
         indptr, cols, vals, sup = s["csr"]
@@ -395,7 +396,8 @@ def run_check(args, rank, world, local_rank):
         else:
             sgd.allreduce_grads(list(agg.parameters()))
         mine = dict(out=out.detach().cpu().numpy(), gx=x_local.grad.cpu().numpy(), gw=agg.weight2.grad.cpu().numpy(),
-                    gb=agg.bias2.grad.cpu().numpy(), dst_lo=s["dst_lo"], nb_lo=lo, n_halo=plan.n_halo, mode=plan.mode,
+                    gb=agg.bias2.grad.cpu().numpy(), dst_lo=s["dst_lo"], nb_lo=lo, n_halo=plan.n_halo,
+                    mode=plan.mode + ("" if plan.mode != "peer" else ("/dense" if plan.dense else "/sparse")),
                     csr=(indptr, cols, vals, sup))
         got = [None] * world
         dist.all_gather_object(got, mine)
@@ -746,16 +748,20 @@ def run_gpu_arm(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_streams)
 
-    modes = {side: s_["plan"].mode for side, s_ in sides.items() if s_["plan"] is not None}
+    modes = {side: s_["plan"].mode + ("" if s_["plan"].mode != "peer" else ("/dense" if s_["plan"].dense else "/sparse"))
+             for side, s_ in sides.items() if s_["plan"] is not None}
     halo_by_side = {side: int(s_["plan"].n_halo) for side, s_ in sides.items() if s_["plan"] is not None}
     if world == 1:
         parallelism = "single GPU"
     else:
         what = (f"each rank owns an {args.workload}-shaped slice of a {world}x larger graph" if args.scaling == "weak" else
                 f"the {args.workload} graph itself cut into {world} contiguous node ranges per side, balanced by nnz")
-        coll = {"peer": "this library's kernels over NVLink peer memory (symmetric buffers): all-gather = every rank stores its "
-                        "block of neighbour rows into every rank's table; reduce-scatter = the transposed gather stores each "
-                        "gradient row into its owner's staging slot + fixed-order local sum; one flag barrier each; no NCCL in the step",
+        coll = {"peer/dense": "this library's kernels over NVLink peer memory (symmetric buffers): all-gather = every rank stores its "
+                              "block of neighbour rows into every rank's table; reduce-scatter = the transposed gather stores each "
+                              "gradient row into its owner's staging slot + fixed-order local sum; one flag barrier each; no NCCL in the step",
+                "peer/sparse": "this library's kernels over NVLink peer memory: all-to-all = one gather launch packs the deduplicated "
+                               "rows each peer asked for and stores them into that peer's halo slots; its transpose = the transposed "
+                               "gather stores every halo gradient into its owner's staging + sorted-transpose sum; no NCCL in the step",
                 "allgather": "NCCL all-gather of the neighbour-row blocks fwd + reduce-scatter bwd (dense halo: every rank needs "
                              "nearly every remote row)",
                 "alltoall": "NCCL all-to-all(v) of deduplicated halo rows fwd + its transpose bwd"}

@@ -197,16 +197,20 @@ int sg_multilink_agg_bwd(float *gx /*n_nb,D*/, const float *gagg /*n_dst,R*D*/, 
  *                       returns.  CUDA-graph replayable (the epoch is device state)
  *   sg_peer_reduce      out (=|+=) stage[0] + stage[1] + ... + stage[world-1] in rank order, slot q at
  *                       stage + q * slot_stride_floats — the local half of the reduce-scatter / all-reduce
- *   sg_multilink_agg_bwd_peer   sg_multilink_agg_bwd whose output row j (global neighbour id) is stored at
- *                       stage[q] + (j - owner_lo[q]) * D for the owner q of j (owner_lo[q] <= j < owner_lo[q+1]):
- *                       the reduce-scatter's transfer happens inside the transposed gather.  D in {16, 32, 64, 128}.
+ *   sg_multilink_agg_bwd_peer   sg_multilink_agg_bwd whose output row j is stored at stage[q] + (j - owner_lo[q]) * D
+ *                       for the target q with owner_lo[q] <= j < owner_lo[q+1] (n_targets <= SG_MAX_PEERS + 1 ranges
+ *                       covering [0, n_nb); empty ranges allowed): the exchange's transfer happens inside the gather.
+ *                       Dense halo: rows = global neighbour ids, one target per rank (the reduce-scatter).  Sparse halo:
+ *                       target 0 = the rank's own rows, then one range of halo slots per peer (the reverse all-to-all);
+ *                       with R = 1, unit weights and one edge per row it is also the forward pack-and-push of the
+ *                       deduplicated halo rows.  D in {16, 32, 64, 128}.
  * ---------------------------------------------------------------------------------------- */
 int sg_peer_push_rows(float *const *dst_host, const float *src, long long n_floats, int world, sg_stream_t stream);
 int sg_peer_barrier(uint32_t *const *flags_host, uint32_t *state, int rank, int world, double timeout_s,
                     sg_stream_t stream);
 int sg_peer_reduce(float *out, const float *stage, long long n_floats, long long slot_stride_floats, int world,
                    int req, sg_stream_t stream);
-int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int world, const float *gagg,
+int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int n_targets, const float *gagg,
                               const float *t_w, const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst,
                               int n_nb, int nnz, int D, const void *t_plan, int plan_chunk, float *partial,
                               sg_stream_t stream);

@@ -97,7 +97,7 @@ __device__ __forceinline__ float *peer_row(const GatherArgs &a, int row) {
   float *base = a.peer_out[0];
   int lo = 0;
 #pragma unroll
-  for (int q = 1; q < SG_MAX_PEERS; ++q)
+  for (int q = 1; q < SG_MAX_PEERS + 1; ++q)
     if (q < a.peer_world && row >= a.peer_lo[q]) { base = a.peer_out[q]; lo = a.peer_lo[q]; }
   return base + (long long)(row - lo) * a.ld_out;
 }
@@ -687,7 +687,7 @@ int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaSt
   }
   if (n_seg == 0 || a.F == 0) return SG_OK;
   if (a.peer_world > 0) {
-    SG_REQUIRE(a.peer_world <= SG_MAX_PEERS && K == 1 && a.n_out_rows == n_seg && a.w && !a.perm && !a.inv_len_indptr &&
+    SG_REQUIRE(a.peer_world <= SG_MAX_PEERS + 1 && K == 1 && a.n_out_rows == n_seg && a.w && !a.perm && !a.inv_len_indptr &&
                    !a.wsum && !a.out_lo && !a.mean && a.req == SG_REQ_WRITE && a.ld_src == a.F && a.ld_out == a.F &&
                    (a.F == 16 || a.F == 32 || a.F == 64 || a.F == 128) && aligned(a.src, 16),
                "peer-scattered output needs the plain weighted fast path (F in 16/32/64/128, write, batch 1)");

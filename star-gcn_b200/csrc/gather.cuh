@@ -48,12 +48,13 @@ struct GatherArgs {
   float *wsum_lo = nullptr;
   int req = SG_REQ_WRITE;
   int mean = 0;  // divide by the segment length (seg_pool 'avg')
-  // peer_world > 0 (node-partitioned backward, peer.cu): output row j belongs to rank q with peer_lo[q] <= j <
-  // peer_lo[q+1] and is stored at peer_out[q] + (j - peer_lo[q]) * ld_out — the owner's staging slot of this rank,
-  // a peer-memory address reached over NVLink; `out` is unused.  Write semantics, n_out_rows == n_seg.
+  // peer_world > 0 (node-partitioned exchange, peer.cu): output row j belongs to TARGET q with peer_lo[q] <= j <
+  // peer_lo[q+1] and is stored at peer_out[q] + (j - peer_lo[q]) * ld_out — a buffer of another rank reached over
+  // NVLink (or a local one); `out` is unused.  Up to SG_MAX_PEERS + 1 targets (the rank's own rows + one range per
+  // peer in the sparse-halo layout).  Write semantics, n_out_rows == n_seg.
   int peer_world = 0;
-  int peer_lo[SG_MAX_PEERS + 1] = {0};
-  float *peer_out[SG_MAX_PEERS] = {nullptr};
+  int peer_lo[SG_MAX_PEERS + 2] = {0};
+  float *peer_out[SG_MAX_PEERS + 1] = {nullptr};
 };
 
 int run_gather(GatherArgs a, int K, int n_seg, int nnz, const void *plan, cudaStream_t st);

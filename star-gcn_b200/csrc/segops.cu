@@ -445,11 +445,12 @@ int sg_multilink_agg_bwd(float *gx, const float *gagg, const float *t_w, const i
   return run_gather(a, 1, n_nb, nnz, t_plan, (cudaStream_t)stream);
 }
 
-int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int world, const float *gagg,
+int sg_multilink_agg_bwd_peer(float *const *stage_host, const int32_t *owner_lo_host, int n_targets, const float *gagg,
                               const float *t_w, const int32_t *t_src, const int32_t *t_indptr, int R, int n_dst,
                               int n_nb, int nnz, int D, const void *t_plan, int plan_chunk, float *partial,
                               sg_stream_t stream) {
-  SG_REQUIRE(world >= 1 && world <= SG_MAX_PEERS, "sg_multilink_agg_bwd_peer: world must be 1..%d", SG_MAX_PEERS);
+  const int world = n_targets;
+  SG_REQUIRE(world >= 1 && world <= SG_MAX_PEERS + 1, "sg_multilink_agg_bwd_peer: n_targets must be 1..%d", SG_MAX_PEERS + 1);
   SG_REQUIRE(R > 0 && n_dst >= 0 && n_nb >= 0 && nnz >= 0 && D > 0, "sg_multilink_agg_bwd_peer: bad sizes");
   SG_REQUIRE(stage_host && owner_lo_host && t_indptr && (nnz == 0 || (gagg && t_w && t_src)),
              "sg_multilink_agg_bwd_peer: null pointer");

@@ -90,11 +90,14 @@ class HaloPlan:
         owner = np.searchsorted(self.owner_ranges, cols, side="right") - 1
         if cols.size and (cols.min() < 0 or cols.max() >= self.owner_ranges[-1]):
             raise ValueError("column id outside the partitioned id space")
-        if mode not in ("auto", "alltoall", "allgather", "peer", "nccl"):
-            raise ValueError("mode must be 'auto', 'nccl', 'alltoall', 'allgather' or 'peer'")
+        if mode not in ("auto", "alltoall", "allgather", "peer", "peer_dense", "peer_sparse", "nccl"):
+            raise ValueError("mode must be 'auto', 'nccl', 'alltoall', 'allgather', 'peer', 'peer_dense' or 'peer_sparse'")
         self._transport = None
-        self.mode = self._choose_mode(mode, cols, owner, index_device, exchange_fn)
-        if self.mode in ("allgather", "peer"):
+        # mode: the transport ('alltoall' / 'allgather' over NCCL, 'peer' = this library's kernels over NVLink peer
+        # memory); dense: the table layout — every row of every rank under its global id, or [local rows ; the
+        # deduplicated halo rows by owner, by id]
+        self.mode, self.dense = self._choose_mode(mode, cols, owner, index_device, exchange_fn)
+        if self.dense:
             # dense halo: every rank fetches (almost) every remote row, so the exchange is an all-gather of the
             # equal-sized blocks and its transpose a reduce-scatter (NVSwitch collectives, no pack / unpack);
             # the concatenated table is indexed by the global ids themselves
@@ -140,23 +143,26 @@ class HaloPlan:
                 raise ValueError(f"rank {q} requested a row this rank does not own")
 
     def _choose_mode(self, mode, cols, owner, index_device, exchange_fn):
-        """'allgather' needs equal blocks, 'peer' (this library's kernels over NVLink peer memory) takes any
-        contiguous ranges; 'auto' picks the dense exchange when at least half of all remote rows are needed by
-        EVERY rank — 'peer' when the ranks are CUDA devices of one box and at most SG_MAX_PEERS, else 'allgather'
-        for equal blocks — and the deduplicated all-to-all otherwise.  'nccl' = 'auto' without the peer transport.
-        Decided collectively so that all ranks take the same path."""
+        """-> (transport, dense layout?).  'allgather' needs equal blocks; 'peer' (this library's kernels over NVLink
+        peer memory) takes any contiguous ranges and both layouts.  A halo is DENSE when at least half of all remote
+        rows are needed by EVERY rank (decided collectively so that all ranks take the same path): 'auto' then uses
+        the global-id table — over peer memory when the ranks are CUDA devices of one box (at most SG_MAX_PEERS), else
+        the NCCL all-gather for equal blocks — and the deduplicated halo rows otherwise (peer memory, else the NCCL
+        all-to-all).  'nccl' = 'auto' without the peer transport; 'peer_dense' / 'peer_sparse' force a layout."""
         sizes = np.diff(self.owner_ranges)
         equal = bool(np.all(sizes == sizes[0]))
         if self.world == 1 or mode == "alltoall":
-            return "alltoall"
+            return "alltoall", False
         if mode == "allgather":
             if not equal:
                 raise ValueError("allgather mode needs equal-sized ownership blocks")
-            return "allgather"
-        if mode == "peer":
-            if self.world > MAX_PEERS:
-                raise ValueError(f"peer mode handles at most {MAX_PEERS} ranks (one NVSwitch box)")
-            return "peer"
+            return "allgather", True
+        if mode in ("peer", "peer_dense", "peer_sparse") and self.world > MAX_PEERS:
+            raise ValueError(f"peer mode handles at most {MAX_PEERS} ranks (one NVSwitch box)")
+        if mode == "peer_dense":
+            return "peer", True
+        if mode == "peer_sparse":
+            return "peer", False
         remote = owner != self.rank
         n_needed = np.unique(cols[remote]).size
         n_remote = int(self.owner_ranges[-1]) - self.n_local
@@ -166,13 +172,13 @@ class HaloPlan:
             flag = torch.tensor([dense], dtype=torch.int32, device=torch.device(index_device))
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             dense = int(flag.item())
-        if not dense:
-            return "alltoall"
-        peer_ok = (mode == "auto" and collective and self.world <= MAX_PEERS and torch.device(index_device).type == "cuda"
-                   and dist.get_backend(self.group) == "nccl")
+        peer_ok = mode == "peer" or (mode == "auto" and collective and self.world <= MAX_PEERS
+                                     and torch.device(index_device).type == "cuda" and dist.get_backend(self.group) == "nccl")
         if peer_ok:
-            return "peer"
-        return "allgather" if equal else "alltoall"
+            return "peer", bool(dense)
+        if dense and equal:
+            return "allgather", True
+        return "alltoall", False
 
     # ---- device-side state for the row exchange ----
     def to(self, device):
@@ -215,12 +221,19 @@ PEER_COPY_ENGINE_BYTES = None
 
 class PeerTransport:
     """Exchange buffers of ONE layer direction in symmetric memory: every rank maps every rank's buffer, so the
-    collectives of the dense-halo case are this library's own kernels over NVLink peer memory (csrc/peer.cu).
+    collectives of the partitioned step are this library's own kernels over NVLink peer memory (csrc/peer.cu).
 
-    Layout of each rank's buffer (fp32 words): [64 flag words | x_ext [n_total, D] | g_stage [world, slot] |
-    w_stage [world, grad_capacity]] — rank p writes block p of every x_ext (forward), slot p of every g_stage /
-    w_stage (backward); the owner sums its slots in rank order.  One stream per direction; see peer.cu for why
-    single buffers suffice."""
+    Layout of each rank's buffer (fp32 words): [64 flag words | x_ext | g_stage | w_stage [world, grad_capacity]].
+      dense halo   x_ext [n_total, D] under global ids: rank p stores block p into every rank's table (all-gather);
+                   g_stage [world, slot]: the transposed gather of rank p stores row j into slot p of j's owner and the
+                   owner sums its slots in rank order (reduce-scatter)
+      sparse halo  x_ext [n_local + n_halo, D]: the rank's own rows, then the DEDUPLICATED rows it needs from every
+                   peer (by owner, by id); one gather launch packs the rows each peer asked for and stores them
+                   straight into that peer's halo slots (all-to-all); g_stage [n_send, D]: the transposed gather stores
+                   the gradient of every halo slot straight into its owner's g_stage at the position of the matching
+                   send slot, and the owner adds them to its rows by the sorted-transpose gather (fixed order)
+    The weight gradient goes through w_stage (push to every rank's slot, sum in rank order).  One stream per
+    direction; see peer.cu for why single buffers suffice."""
     FLAG_WORDS = 64
 
     def __init__(self, plan, D, grad_floats, device, timeout_s=10.0):
@@ -229,49 +242,93 @@ class PeerTransport:
         from . import _lib
         self._lib, self._ctypes = _lib, ctypes
         self.plan, self.D, self.timeout_s = plan, int(D), float(timeout_s)
-        self.rank, self.world = plan.rank, plan.world
+        self.rank, self.world, self.dense = plan.rank, plan.world, bool(plan.dense)
         self.device = torch.device(device)
         if self.world > MAX_PEERS:
             raise ValueError(f"peer transport handles at most {MAX_PEERS} ranks")
-        W, rank = self.world, self.rank
+        W, rank, D = self.world, self.rank, self.D
         lo = [int(v) for v in plan.owner_ranges]
         self.n_total, self.n_local = lo[-1], lo[rank + 1] - lo[rank]
+        group = plan.group if plan.group is not None else dist.group.WORLD
 
         def al(n):
             return (int(n) + 63) // 64 * 64
 
-        self.slot = al(max(b - a for a, b in zip(lo[:-1], lo[1:])) * self.D)
+        if self.dense:
+            x_rows, g_floats = self.n_total, None
+            self.slot = al(max(b - a for a, b in zip(lo[:-1], lo[1:])) * D)
+            g_floats = W * self.slot
+        else:
+            # every rank's counts: recv[p][q] = rows p fetches from q (= rows q sends to p)
+            mine = dict(n_local=self.n_local, recv=[int(c) for c in plan.recv_counts], send=[int(c) for c in plan.send_counts])
+            allc = [None] * W
+            dist.all_gather_object(allc, mine, group=group)
+            for p_ in range(W):
+                for q in range(W):
+                    if allc[p_]["recv"][q] != allc[q]["send"][p_]:
+                        raise RuntimeError("halo plans of the ranks do not match (recv / send counts differ)")
+            self._counts = allc
+            x_rows = max(c["n_local"] + sum(c["recv"]) for c in allc)      # symmetric allocation: the largest rank's size
+            g_floats = al(max(sum(c["send"]) for c in allc) * D)
+            self.n_ext = self.n_local + sum(mine["recv"])
+            self.n_send = sum(mine["send"])
         self.grad_capacity = al(grad_floats)
         off, pos = {}, self.FLAG_WORDS
-        for name, n in (("x_ext", al(self.n_total * self.D)), ("g_stage", W * self.slot), ("w_stage", W * self.grad_capacity)):
+        for name, n in (("x_ext", al(x_rows * D)), ("g_stage", g_floats), ("w_stage", W * self.grad_capacity)):
             off[name], pos = pos, pos + n
         self.off = off
-        group = plan.group if plan.group is not None else dist.group.WORLD
         self.buf = symm.empty(pos, dtype=torch.float32, device=self.device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
         base = [int(b) for b in self.handle.buffer_ptrs]
         if len(base) != W or base[rank] != self.buf.data_ptr():
             raise RuntimeError("symmetric-memory rendezvous returned an unexpected pointer table")
+        self._base = base
         self.state = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)            # every rank's flag words are zero before anyone can arrive
 
         def table(vals):
-            return (ctypes.c_void_p * W)(*vals)
+            return (ctypes.c_void_p * len(vals))(*vals)
 
+        self._table = table
         self._flags = table(base)
-        self._x_dst = table([b + 4 * (off["x_ext"] + lo[rank] * self.D) for b in base])
-        self._g_dst = table([b + 4 * (off["g_stage"] + rank * self.slot) for b in base])
         self._w_dst = table([b + 4 * (off["w_stage"] + rank * self.grad_capacity) for b in base])
-        self._owner_lo = (ctypes.c_int32 * (W + 1))(*lo)
-        self.x_ext = self.buf[off["x_ext"]:off["x_ext"] + self.n_total * self.D].view(self.n_total, self.D)
-        self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + W * self.slot]
         self._w_stage = self.buf[off["w_stage"]:off["w_stage"] + W * self.grad_capacity]
+        if self.dense:
+            self._x_dst = table([b + 4 * (off["x_ext"] + lo[rank] * D) for b in base])
+            self._g_dst = table([b + 4 * (off["g_stage"] + rank * self.slot) for b in base])
+            self._owner_lo = (ctypes.c_int32 * (W + 1))(*lo)
+            self.x_ext = self.buf[off["x_ext"]:off["x_ext"] + self.n_total * D].view(self.n_total, D)
+            self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + W * self.slot]
+            # this rank's block inside every rank's table, as tensors (copy-engine path of all_gather)
+            self._x_peer = [self.handle.get_buffer(q, (self.n_local, D), torch.float32, off["x_ext"] + lo[rank] * D)
+                            for q in range(W)]
+        else:
+            allc = self._counts
+            self.x_ext = self.buf[off["x_ext"]:off["x_ext"] + self.n_ext * D].view(self.n_ext, D)
+            self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + max(self.n_send, 1) * D].view(max(self.n_send, 1), D)[:self.n_send]
+            # forward: send slot s of the block for peer p lands in p's table behind p's own rows and the rows p
+            # fetches from lower ranks
+            send_lo = [0]
+            for p_ in range(W):
+                send_lo.append(send_lo[-1] + allc[rank]["send"][p_])
+            self._send_lo = (ctypes.c_int32 * (W + 1))(*send_lo)
+            self._x_dst = table([base[p_] + 4 * (off["x_ext"] + (allc[p_]["n_local"] + sum(allc[p_]["recv"][:rank])) * D)
+                                 for p_ in range(W)])
+            # backward: rows [0, n_local) stay here (target 0, set per call); the halo slots fetched from owner q go to
+            # q's g_stage at the position of the block q sends to this rank
+            halo_lo = [0, self.n_local]
+            for q in range(W):
+                halo_lo.append(halo_lo[-1] + allc[rank]["recv"][q])
+            self._halo_lo = (ctypes.c_int32 * (W + 2))(*halo_lo)
+            self._g_dst_peers = [base[q] + 4 * (off["g_stage"] + sum(allc[q]["send"][:rank]) * D) for q in range(W)]
+            d = plan._dev if plan._dev is not None else plan.to(self.device)._dev
+            self._send_cat = d["send_cat"]
+            self._send_ptr = torch.arange(self.n_send + 1, dtype=torch.int32, device=self.device)
+            self._send_ones = torch.ones(max(self.n_send, 1), dtype=torch.float32, device=self.device)
         self._open = False                   # a forward whose consumers no barrier has covered yet
-        # this rank's block inside every rank's table, as tensors (copy-engine path of all_gather)
-        self._x_peer = [self.handle.get_buffer(q, (self.n_local, self.D), torch.float32, off["x_ext"] + lo[rank] * self.D)
-                        for q in range(W)]
+        self._g_self = None
 
     def _prof(self, tag, fn):
         from . import graph
@@ -292,23 +349,37 @@ class PeerTransport:
             "sg_peer_barrier"))
 
     def all_gather(self, x_local, will_backward):
-        """x_local [n_local, D] -> the [n_total, D] table of every rank (a view of the symmetric buffer, valid until
-        the next all_gather).  ``will_backward``: the backward's barrier will cover this table's readers; otherwise
-        the caller ends its forward with :meth:`release`."""
+        """x_local [n_local, D] -> this rank's table x_ext (a view of the symmetric buffer, valid until the next
+        call): [n_total, D] under global ids (dense) or [own rows ; deduplicated halo rows] (sparse).
+        ``will_backward``: the backward's barrier will cover this table's readers; otherwise the caller ends its
+        forward with :meth:`release`."""
         if x_local.shape != (self.n_local, self.D) or x_local.dtype != torch.float32 or not x_local.is_contiguous():
             raise ValueError(f"x_local must be a contiguous float32 [{self.n_local}, {self.D}] tensor")
         if self._open:                       # the previous forward never reached a covering barrier
             self.barrier()
-        lib = self._lib.load()
+        lib, c = self._lib.load(), self._ctypes
+        n = self.n_local * self.D
 
-        def push():
-            if PEER_COPY_ENGINE_BYTES is not None and 4 * self.n_local * self.D >= PEER_COPY_ENGINE_BYTES:
+        def push_dense():
+            if PEER_COPY_ENGINE_BYTES is not None and 4 * n >= PEER_COPY_ENGINE_BYTES:
                 for k in range(self.world):          # start with the next rank so that the links are used evenly
                     self._x_peer[(self.rank + 1 + k) % self.world].copy_(x_local, non_blocking=True)
             else:
-                self._lib.check(lib.sg_peer_push_rows(self._x_dst, self._ptr(x_local), self.n_local * self.D, self.world,
-                                                      self._stream()), "sg_peer_push_rows")
-        self._prof("peer_push", push)
+                self._lib.check(lib.sg_peer_push_rows(self._x_dst, self._ptr(x_local), n, self.world, self._stream()),
+                                "sg_peer_push_rows")
+
+        def push_sparse():
+            # own rows: a local copy; requested rows: ONE gather launch (one edge per send slot, unit weights) whose
+            # output rows are stored straight into the requesting ranks' halo slots
+            own = self._table([self.x_ext.data_ptr()])
+            self._lib.check(lib.sg_peer_push_rows(own, self._ptr(x_local), n, 1, self._stream()), "sg_peer_push_rows")
+            if self.n_send:
+                self._lib.check(lib.sg_multilink_agg_bwd_peer(
+                    self._x_dst, self._send_lo, self.world, self._ptr(x_local), self._ptr(self._send_ones),
+                    self._ptr(self._send_cat), self._ptr(self._send_ptr), 1, self.n_local, self.n_send, self.n_send, self.D,
+                    c.c_void_p(0), 0, c.c_void_p(0), self._stream()), "sg_multilink_agg_bwd_peer (pack + push)")
+
+        self._prof("peer_push", push_dense if self.dense else push_sparse)
         self.barrier()
         self._open = True
         return self.x_ext
@@ -328,18 +399,34 @@ class PeerTransport:
                         "sg_peer_push_rows")
 
     def scatter_args(self):
-        """(stage pointer table, ownership ranges, world) for sg_multilink_agg_bwd_peer."""
-        return self._g_dst, self._owner_lo, self.world
+        """(target pointer table, row ranges, number of targets) for sg_multilink_agg_bwd_peer — where the transposed
+        gather stores the gradient row of every table row."""
+        if self.dense:
+            return self._g_dst, self._owner_lo, self.world
+        # target 0: this rank's own rows, written locally into the tensor reduce_rows() will return
+        self._g_self = torch.empty((self.n_local, self.D), dtype=torch.float32, device=self.device)
+        targets = [self._g_self.data_ptr() if self.n_local else self.x_ext.data_ptr()] + self._g_dst_peers
+        self._targets = self._table(targets)         # kept alive until the launch has been issued
+        return self._targets, self._halo_lo, self.world + 1
 
     def reduce_rows(self):
-        """Sum of the world staging slots of this rank's rows, in rank order -> [n_local, D]."""
-        out = torch.empty((self.n_local, self.D), dtype=torch.float32, device=self.device)
-        if self.n_local:
-            lib = self._lib.load()
-            n = self.n_local * self.D
-            self._prof("peer_reduce", lambda: self._lib.check(
-                lib.sg_peer_reduce(self._ptr(out), self._ptr(self._g_stage), n, self.slot, self.world, 1, self._stream()),
-                "sg_peer_reduce"))
+        """Gradient of this rank's own rows after the backward barrier -> [n_local, D].  Dense: the world staging
+        slots summed in rank order.  Sparse: the locally written rows + the halo gradients the peers stored into
+        g_stage, added by the sorted-transpose gather over the send pattern (fixed order)."""
+        lib = self._lib.load()
+        if self.dense:
+            out = torch.empty((self.n_local, self.D), dtype=torch.float32, device=self.device)
+            if self.n_local:
+                n = self.n_local * self.D
+                self._prof("peer_reduce", lambda: self._lib.check(
+                    lib.sg_peer_reduce(self._ptr(out), self._ptr(self._g_stage), n, self.slot, self.world, 1, self._stream()),
+                    "sg_peer_reduce"))
+            return out
+        out, self._g_self = self._g_self, None
+        if self.n_send and self.n_local:
+            pat = self.plan.send_pattern()
+            self._prof("peer_reduce", lambda: seg_op._weighted_pool_bwd_data(
+                self._g_stage.unsqueeze(0), self.plan._dev["ones"], pat, self.n_local, out=out.unsqueeze(0), req="add"))
         return out
 
     def reduce_grad(self, g_flat):

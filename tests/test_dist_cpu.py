@@ -44,8 +44,12 @@ def _worker(rank, world, port, q):
             ok_auto = auto.mode == "allgather" and auto.n_ext == xg.shape[0] and np.array_equal(auto.local_cols, cols)
             # the peer-memory mode keeps global ids as well (any contiguous ranges; the kernels need CUDA, the plan does not)
             peer = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="peer")
-            ok_auto = (ok_auto and peer.mode == "peer" and peer.n_ext == xg.shape[0] and np.array_equal(peer.local_cols, cols)
-                       and peer.n_local == ranges[rank + 1] - ranges[rank])
+            ok_auto = (ok_auto and peer.mode == "peer" and peer.dense and peer.n_ext == xg.shape[0]
+                       and np.array_equal(peer.local_cols, cols) and peer.n_local == ranges[rank + 1] - ranges[rank])
+            # ... and its sparse layout is the all-to-all plan: [own rows ; deduplicated halo rows by owner, by id]
+            sparse = sgd.HaloPlan(cols, ranges, rank, world, index_device="cpu", mode="peer_sparse")
+            ok_auto = (ok_auto and sparse.mode == "peer" and not sparse.dense and np.array_equal(sparse.local_cols, plan.local_cols)
+                       and sparse.send_counts == plan.send_counts and sparse.recv_counts == plan.recv_counts)
             lo, hi = ranges[rank], ranges[rank + 1]
             x_local = torch.from_numpy(xg[lo:hi])
             # row exchange emulated with a gloo all-to-all on CPU tensors (test stand-in for pack kernel + NCCL)

@@ -143,6 +143,7 @@ def test_partitioned_step_over_nccl_matches_whole_graph():
                        capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert line["ok"] and set(line["cases"]) == {"weak/alltoall", "weak/allgather", "strong/alltoall", "weak/peer", "strong/peer"}
+    assert line["ok"] and set(line["cases"]) == {"weak/alltoall", "weak/allgather", "strong/alltoall", "weak/peer", "strong/peer",
+                                                      "weak/peer_sparse", "strong/peer_sparse"}
     for case in line["cases"].values():
         assert case["ok"] and max(case["out"], case["gx"], case["gw"], case["gb"]) <= 1e-5

@@ -117,3 +117,34 @@ def test_transposed_gather_scatters_rows_to_owner_slots(D):
     with pytest.raises(ValueError):                   # ranges must cover [0, n_nb)
         L.check(lib.sg_multilink_agg_bwd_peer(_table([s.data_ptr() for s in stages]), (ctypes.c_int32 * (world + 1))(0, 17, 60, n_nb - 1),
                                               world, *args, *tail), "agg_bwd_peer")
+
+
+def test_pack_and_push_rows_with_empty_and_nine_targets():
+    """The sparse-halo forward: one gather launch (one edge per send slot, unit weights, R = 1, no schedule) packs the
+    requested rows and stores each block into its target's buffer — SG_MAX_PEERS + 1 targets, some of them empty."""
+    L, lib = _lib()
+    dev = torch.device("cuda")
+    D, n_local = 64, 500
+    rs = np.random.RandomState(4)
+    x = torch.from_numpy(rs.normal(size=(n_local, D)).astype(np.float32)).to(dev)
+    counts = [7, 0, 33, 0, 0, 120, 1, 64, 12]                       # 9 targets
+    lo = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n_send = int(lo[-1])
+    send = torch.from_numpy(rs.randint(0, n_local, n_send).astype(np.int32)).to(dev)
+    ptr = torch.arange(n_send + 1, dtype=torch.int32, device=dev)
+    ones = torch.ones(n_send, device=dev)
+    bufs = [torch.full((max(c, 1), D), float("nan"), device=dev) for c in counts]
+    L.check(lib.sg_multilink_agg_bwd_peer(_table([b.data_ptr() for b in bufs]), (ctypes.c_int32 * 10)(*lo.tolist()), 9,
+                                          ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(ones.data_ptr()), ctypes.c_void_p(send.data_ptr()),
+                                          ctypes.c_void_p(ptr.data_ptr()), 1, n_local, n_send, n_send, D, None, 0, None, None), "pack+push")
+    torch.cuda.synchronize()
+    for q, c in enumerate(counts):
+        if c:
+            assert torch.equal(bufs[q][:c], x[send[lo[q]:lo[q + 1]].long()])
+        else:
+            assert torch.isnan(bufs[q]).all()                        # an empty range receives nothing
+    with pytest.raises(ValueError):                                  # more than SG_MAX_PEERS + 1 targets
+        L.check(lib.sg_multilink_agg_bwd_peer(_table([b.data_ptr() for b in bufs] + [bufs[0].data_ptr()]),
+                                              (ctypes.c_int32 * 11)(*lo.tolist(), n_send), 10,
+                                              ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(ones.data_ptr()), ctypes.c_void_p(send.data_ptr()),
+                                              ctypes.c_void_p(ptr.data_ptr()), 1, n_local, n_send, n_send, D, None, 0, None, None), "pack+push")
