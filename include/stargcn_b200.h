@@ -49,7 +49,7 @@ long long sg_launch_count(void);
 void sg_launch_count_reset(void);
 /* Development only (tools/, A/B measurements): set a process-wide tuning option; 0 is always the shipped
  * behaviour and the product path never calls this.  Options: 0 gather variant (1 = bulk-copy staged segments),
- * 1 gather blocks per SM, 2 GEMM TMEM hand-back arrival (1 = release), 3 GEMM chain length in k-blocks, 4 threads per block of the fast gather launches,
+ * 1 gather blocks per SM, 2 GEMM TMEM hand-back arrival (1 = release), 3 GEMM chain length in k-blocks, 4 threads per block of the fast gather launches, 5 quarter-blocks per SM of the all-gather store kernel,
  * 8 GEMM wait-cycle trace (sg_gemm_trace_read).  Nothing in the library reads the environment. */
 int sg_dev_option(int which, int value);
 

@@ -118,7 +118,7 @@ def check(rc, what):
         raise StarGCNError(f"{what} failed (code {rc}): {msg}")
 
 
-DEV_OPTIONS = {"gather_variant": 0, "gather_grid": 1, "gemm_arrive": 2, "gemm_chain": 3, "gather_threads": 4, "gemm_trace": 8}
+DEV_OPTIONS = {"gather_variant": 0, "gather_grid": 1, "gemm_arrive": 2, "gemm_chain": 3, "gather_threads": 4, "peer_push_blocks": 5, "gemm_trace": 8}
 
 
 def dev_option(name, value):

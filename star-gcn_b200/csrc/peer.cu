@@ -136,7 +136,8 @@ int sg_peer_push_rows(float *const *dst_host, const float *src, long long n_floa
   }
   const long long n4 = n_floats / 4;
   long long blocks = ceil_div<long long>(n4, 256 * 4);
-  const long long cap = 2LL * num_sms();   // the stores are posted: two blocks per SM keep the NVLink ports busy
+  const int dv = dev_option(SG_DEV_PEER_PUSH_BLOCKS);
+  const long long cap = (dv > 0 ? dv : 8) * (long long)num_sms() / 4;   // the stores are posted: two blocks per SM keep the NVLink ports busy
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   peer_push_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const float4 *>(src), n4, world);

@@ -17,6 +17,7 @@ for w in $WHAT; do
     sm)     el "weak, peer transport, all-gather by the store kernel"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --peer-push sm --steps 100 --warmup 10 2> $O/sm_n$N.err > $O/sm_n$N.json; python tools/bench_summary.py < $O/sm_n$N.json ;;
     ce)     el "weak, peer transport, all-gather by copy engines"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --peer-push ce --steps 100 --warmup 10 2> $O/ce_n$N.err > $O/ce_n$N.json; python tools/bench_summary.py < $O/ce_n$N.json ;;
     psparse) el "weak, peer transport, sparse-halo layout forced"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode peer_sparse --steps 100 --warmup 10 2> $O/psparse_n$N.err > $O/psparse_n$N.json; python tools/bench_summary.py < $O/psparse_n$N.json ;;
+    push*)  v=${w#push}; el "weak, peer, all-gather store kernel with $v quarter-blocks per SM"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --dev peer_push_blocks=$v --steps 100 --warmup 10 2> $O/push${v}_n$N.err > $O/push${v}_n$N.json; python tools/bench_summary.py < $O/push${v}_n$N.json | head -1 ;;
     check)  el "check"; run bench.py --gpus $N --check 2> $O/check_n$N.err | tee $O/check_n$N.json | cut -c1-900 ;;
     weak)   el "weak (auto exchange)"; run bench.py --gpus $N --no-cpu-baseline --steps 100 --warmup 10 2> $O/weak_n$N.err > $O/weak_n$N.json; python tools/bench_summary.py < $O/weak_n$N.json ;;
     a2a)    el "weak, all-to-all forced"; run bench.py --gpus $N --no-cpu-baseline --no-e2e --halo-mode alltoall --steps 100 --warmup 10 2> $O/a2a_n$N.err > $O/a2a_n$N.json; python tools/bench_summary.py < $O/a2a_n$N.json ;;
