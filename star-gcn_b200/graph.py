@@ -10,7 +10,6 @@ schedules that the backward pass needs, and stay resident for every forward/back
 uses the plan.
 """
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -537,8 +536,6 @@ class _PackWExt(torch.autograd.Function):
 
 def pack_w_ext(ws, bs):
     """[W_0 | ... | W_{R-1} | b_0 ... b_{R-1}] — the B operand of the fused transform (see _PackWExt)."""
-    if os.environ.get("SG_PACK_FUSED", "1") == "0":       # A/B switch: autograd's own cat/stack backward
-        return torch.cat(list(ws) + [torch.stack(list(bs), dim=1)], dim=1)
     return _PackWExt.apply(len(ws), *ws, *bs)
 
 
