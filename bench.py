@@ -542,6 +542,9 @@ def run_gpu_arm(args, rank, world, local_rank):
             side_group = dist.new_group(backend="nccl")
             plan = sgd.HaloPlan(cols, ps["nb_ranges"], rank, world, group=side_group, index_device=dev,
                                 mode=args.halo_mode).to(dev)
+            if plan.mode == "peer" and not plan.try_peer_transport(D, U * (R * D + R), dev):
+                # no symmetric memory on this box: the NCCL collectives carry the exchange instead
+                plan = sgd.HaloPlan(cols, ps["nb_ranges"], rank, world, group=side_group, index_device=dev, mode="nccl").to(dev)
             lists = synth.split_by_level(indptr, plan.local_cols, vals, sup, wl["base"]["levels"])[:3]
             csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev).prepare(backward=True)
             x_np = rng.standard_normal((plan.n_local, D), dtype=np.float32)

@@ -151,18 +151,18 @@ class HaloPlan:
         all-to-all).  'nccl' = 'auto' without the peer transport; 'peer_dense' / 'peer_sparse' force a layout."""
         sizes = np.diff(self.owner_ranges)
         equal = bool(np.all(sizes == sizes[0]))
-        if self.world == 1 or mode == "alltoall":
-            return "alltoall", False
-        if mode == "allgather":
-            if not equal:
-                raise ValueError("allgather mode needs equal-sized ownership blocks")
-            return "allgather", True
         if mode in ("peer", "peer_dense", "peer_sparse") and self.world > MAX_PEERS:
             raise ValueError(f"peer mode handles at most {MAX_PEERS} ranks (one NVSwitch box)")
         if mode == "peer_dense":
             return "peer", True
         if mode == "peer_sparse":
             return "peer", False
+        if self.world == 1 or mode == "alltoall":
+            return "alltoall", False
+        if mode == "allgather":
+            if not equal:
+                raise ValueError("allgather mode needs equal-sized ownership blocks")
+            return "allgather", True
         remote = owner != self.rank
         n_needed = np.unique(cols[remote]).size
         n_remote = int(self.owner_ranges[-1]) - self.n_local
@@ -200,6 +200,26 @@ class HaloPlan:
     @property
     def halo_bytes_per_row_float(self):
         return 4 * self.n_halo
+
+    def try_peer_transport(self, D, grad_floats, device):
+        """Create the peer transport NOW and agree collectively that every rank succeeded.  Returns True, or False
+        after resetting nothing — the caller then rebuilds its plans with ``mode='nccl'`` (symmetric memory needs
+        peer-to-peer capable CUDA devices of one box; anything else falls back to the NCCL collectives)."""
+        ok = 1
+        try:
+            self.peer_transport(D, grad_floats, device)
+        except Exception as e:                      # noqa: BLE001 — any failure means "no peer memory here"
+            import sys
+            print(f"[stargcn_b200.dist] rank {self.rank}: peer-memory transport unavailable ({type(e).__name__}: {e}); "
+                  f"falling back to NCCL", file=sys.stderr)
+            self._transport, ok = None, 0
+        if dist.is_initialized() and self.world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=torch.device(device))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = int(flag.item())
+        if not ok:
+            self._transport = None
+        return bool(ok)
 
     def peer_transport(self, D, grad_floats, device):
         """The symmetric-memory buffers of this direction (mode 'peer'), created collectively on first use."""

@@ -148,3 +148,68 @@ def test_pack_and_push_rows_with_empty_and_nine_targets():
                                               (ctypes.c_int32 * 11)(*lo.tolist(), n_send), 10,
                                               ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(ones.data_ptr()), ctypes.c_void_p(send.data_ptr()),
                                               ctypes.c_void_p(ptr.data_ptr()), 1, n_local, n_send, n_send, D, None, 0, None, None), "pack+push")
+
+
+def _single_rank_worker(port, q):
+    """world = 1 process group: the PeerTransport class end to end on one device (symmetric allocation, pointer tables,
+    push / barrier / scatter / reduce launches inside the fused op, forward-only release) against the plain layer."""
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        from stargcn_b200 import dist as sgd, synth
+        from stargcn_b200.graph import MultiLinkCSR
+        from stargcn_b200.layers import MultiLinkGCNAggregator
+        dev = torch.device("cuda", 0)
+        R, D, U = 5, 64, 250
+        base = synth.make_bipartite(300, 200, 6000, n_levels=R, seed=3)
+        c = base["u2i"]
+        res = {}
+        for mode in ("peer_dense", "peer_sparse"):
+            plan = sgd.HaloPlan(c["cols"], np.array([0, base["n_item"]]), 0, 1, index_device=dev, mode=mode).to(dev)
+            assert plan.mode == "peer" and plan.n_ext == base["n_item"] and plan.n_halo == 0
+            lists = synth.split_by_level(c["indptr"], plan.local_cols, c["vals"], c["support"], base["levels"])[:3]
+            csr = MultiLinkCSR(*lists, n_nb=plan.n_ext, device=dev)
+            torch.manual_seed(1)
+            agg = MultiLinkGCNAggregator(units=U, num_links=R, act="leaky", accum="sum", in_units=D).to(dev)
+            x = torch.randn((base["n_item"], D), device=dev, requires_grad=True)
+            gout = torch.randn((base["n_user"], U), device=dev)
+            ref = agg(x, csr)
+            ref.backward(gout)
+            want = (ref.detach().clone(), x.grad.clone(), agg.weight1.grad.clone())
+            x.grad = None
+            agg.zero_grad(set_to_none=True)
+            agg.grad_group = dist.group.WORLD
+            with torch.no_grad():
+                out0 = sgd.partitioned_aggregate(agg, x, plan, csr)            # forward-only: ends with release()
+            for _ in range(2):                                                   # buffers reused
+                x.grad = None
+                agg.zero_grad(set_to_none=True)
+                out = sgd.partitioned_aggregate(agg, x, plan, csr)
+                out.backward(gout)
+            plan._transport.check()
+            res[mode] = bool(torch.equal(out0, want[0]) and torch.equal(out, want[0]) and torch.equal(x.grad, want[1])
+                             and torch.equal(agg.weight1.grad, want[2]))
+        q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_peer_transport_single_rank_equals_plain_layer():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_single_rank_worker, args=(port, q))
+    p.start()
+    res = q.get(timeout=240)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    assert res == {"peer_dense": True, "peer_sparse": True}
