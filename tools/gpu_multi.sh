@@ -1,6 +1,8 @@
 #!/bin/bash
-# One `gpurun --gpus N` call: NCCL parity check + the partitioned bench in its three shapes.
-# Usage: bash tools/gpu_multi.sh N [check|weak|a2a|strong ...]   (default: all four)
+# One `gpurun --gpus N` call: parity check of every exchange transport + the partitioned bench.
+# Usage: bash tools/gpu_multi.sh N [peertest|check|weak|nccl|a2a|psparse|strong|strongnccl|sm|ce|pushK ...]
+#   weak / strong = default transport (peer memory); nccl / strongnccl / a2a = the NCCL collectives; psparse = peer memory
+#   with the sparse-halo layout forced; sm / ce = all-gather by the store kernel / copy engines; pushK = store-kernel grid
 set -u
 N=${1:-2}; shift || true
 WHAT=${*:-check weak a2a strong}
