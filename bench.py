@@ -841,7 +841,9 @@ def run_e2e(args, wl, sides, dev, world, barrier, total_edges, all_params, side_
 
     # double-buffered prefetch: while step i computes, step i+1's inputs cross PCIe on a copy stream
     # (what a loader thread does); every step still copies all of its inputs inside the timed region
-    copy_stream = torch.cuda.Stream(device=dev)
+    # high priority: the upload kernel of small plans (sg_upload_segments) must get SM slots WHILE the previous step's
+    # graph fills the GPU, otherwise it queues behind it and copy and compute serialise (DMA copies do not care)
+    copy_stream = torch.cuda.Stream(device=dev, priority=-1)
     main = torch.cuda.current_stream()
     consumers = [main] + list(side_streams or [])
     slots = [None, None]
@@ -951,7 +953,9 @@ def _e2e_static_slots(args, wl, sides, dev, barrier, total_edges, side_streams, 
     import torch
     from stargcn_b200 import runtime
     from stargcn_b200.graph import MultiLinkCSR
-    copy_stream = torch.cuda.Stream(device=dev)
+    # high priority: the upload kernel of small plans (sg_upload_segments) must get SM slots WHILE the previous step's
+    # graph fills the GPU, otherwise it queues behind it and copy and compute serialise (DMA copies do not care)
+    copy_stream = torch.cuda.Stream(device=dev, priority=-1)
     main = torch.cuda.current_stream()
     slots = []
     for _ in range(2):

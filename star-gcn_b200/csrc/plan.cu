@@ -386,25 +386,42 @@ static int key_bits(int n_nb) {
 // ------------------------------------------------------------------------------------------
 // Upload of many small host arrays in ONE launch: the per-level lists of a plan (3 * R arrays per direction,
 // mxgraph/layers/layers.py:366-377 uploads each with its own nd.array call) sit in PINNED host memory, which a
-// kernel can read directly (unified addressing): every thread copies 4-byte elements of the flattened segment
-// list, a warp request is 128 contiguous bytes of one host array.  For the small plans of ML-100k / Douban-sized
+// kernel can read directly (unified addressing): every thread copies one 16-byte unit of the flattened segment
+// list, a warp request is 512 contiguous bytes of one host array.  For the small plans of ML-100k / Douban-sized
 // graphs this replaces ~60 DMA set-ups (~10 us each) by one ~20 us kernel; large plans keep the copy engines.
 // ------------------------------------------------------------------------------------------
 constexpr int kUploadMaxSeg = 64;
 struct UploadArgs {
   const uint32_t *src[kUploadMaxSeg];
   uint32_t *dst[kUploadMaxSeg];
-  long long end[kUploadMaxSeg];   // cumulative element counts
+  long long end[kUploadMaxSeg];   // cumulative counts of 16-byte units (4 words; the last unit of a segment may be partial)
+  long long words[kUploadMaxSeg]; // 4-byte words of the segment
   int n;
 };
 
+// `end` counts UNITS of four 4-byte words per segment (the last unit of a segment may be partial): a thread reads one
+// unit with ONE 16-byte load when the host array allows it (16-byte aligned base — pinned allocations are) — a warp
+// request is then 512 contiguous bytes of host memory instead of 128, which is what the PCIe read path wants — and
+// stores it with one 16-byte store when the device slice is aligned too, else word by word.
 __global__ void __launch_bounds__(256) upload_segments_kernel(const __grid_constant__ UploadArgs a) {
   const long long total = a.end[a.n - 1];
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int k = 0;
     while (t >= a.end[k]) ++k;            // n <= 64 segments: a short scan, uniform inside a warp except at seams
-    const long long o = t - (k ? a.end[k - 1] : 0);
-    a.dst[k][o] = a.src[k][o];
+    const long long u = t - (k ? a.end[k - 1] : 0);
+    const long long w0 = u * 4, nw = a.words[k];
+    const uint32_t *src = a.src[k] + w0;
+    uint32_t *dst = a.dst[k] + w0;
+    if (w0 + 4 <= nw && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(src);
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(dst) = v;
+      } else {
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    } else {
+      for (int j = 0; j < 4 && w0 + j < nw; ++j) dst[j] = src[j];
+    }
   }
 }
 
@@ -558,14 +575,15 @@ int sg_upload_segments(void *const *dst_device, const void *const *src_pinned_ho
       SG_REQUIRE((bytes[k] & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_device[k]) & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(src_pinned_host[k]) & 3) == 0,
                  "sg_upload_segments: segments must be 4-byte aligned multiples of 4 bytes");
-      total += (long long)(bytes[k] / 4);
+      a.words[a.n] = (long long)(bytes[k] / 4);
+      total += (a.words[a.n] + 3) / 4;
       a.src[a.n] = static_cast<const uint32_t *>(src_pinned_host[k]);
       a.dst[a.n] = static_cast<uint32_t *>(dst_device[k]);
       a.end[a.n] = total;
       ++a.n;
     }
     if (a.n == 0) continue;
-    long long blocks = ceil_div<long long>(total, 256 * 4);
+    long long blocks = ceil_div<long long>(total, 256);   // one 16-byte unit per thread: every request in flight at once
     const long long cap = (long long)num_sms() * 4;      // enough requests in flight for PCIe, few SMs taken
     if (blocks > cap) blocks = cap;
     upload_segments_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);

@@ -102,3 +102,28 @@ def test_refresh_in_place_and_graph_replay():
     assert torch.equal(a.end_points, fresh_b.end_points) and torch.equal(a.cat_indptr, fresh_b.cat_indptr)
     with pytest.raises(ValueError):
         a.load_lists_(ep_b, ptr_l, sup_b, zero_copy=True)          # pageable numpy arrays cannot be read by the kernel
+
+
+def test_upload_segments_ragged_lengths_and_misaligned_slices():
+    """sg_upload_segments: 16-byte units with partial tails, device slices at arbitrary 4-byte offsets, host arrays that
+    are NOT 16-byte aligned (word-by-word path), empty segments, and more segments than one launch holds."""
+    import ctypes
+    from stargcn_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    lens = [1, 2, 3, 4, 5, 7, 8, 0, 31, 32, 33, 1000, 4097] + [int(v) for v in rs.randint(0, 300, size=70)]   # 83 segments
+    host = torch.from_numpy(rs.randint(-2 ** 31, 2 ** 31 - 1, size=sum(lens) + 4 * len(lens) + 8, dtype=np.int64).astype(np.int32)).pin_memory()
+    dev = torch.full((sum(lens) + 3 * len(lens) + 8,), -7, dtype=torch.int32, device="cuda")
+    srcs, dsts, nbytes, want = [], [], [], dev.clone()
+    ho, do = 0, 1
+    for i, n in enumerate(lens):
+        ho += i % 4                         # host sub-array starts at every 4-byte phase of a 16-byte line
+        do += (i * 3) % 4 + (1 if i % 5 == 0 else 0)
+        srcs.append(host.data_ptr() + 4 * ho); dsts.append(dev.data_ptr() + 4 * do); nbytes.append(4 * n)
+        want[do:do + n] = host[ho:ho + n].cuda()
+        ho += n; do += n
+    n = len(lens)
+    _lib.check(lib.sg_upload_segments((ctypes.c_void_p * n)(*dsts), (ctypes.c_void_p * n)(*srcs), (ctypes.c_size_t * n)(*nbytes), n, None),
+               "sg_upload_segments")
+    torch.cuda.synchronize()
+    assert torch.equal(dev, want)           # every word where it belongs, nothing outside the slices touched
