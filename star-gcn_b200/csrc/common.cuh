@@ -58,7 +58,7 @@ enum DevOption {
   SG_DEV_GEMM_ARRIVE = 2,      // 1: cluster-scope RELEASE arrival when a TMEM buffer is handed back (0 = relaxed)
   SG_DEV_GEMM_CHAIN = 3,       // k-blocks per TMEM accumulation chain (0 = kChainKBlocks)
   SG_DEV_GATHER_THREADS = 4,   // threads per block of the fast gather launches (0 = the shipped size; 128 / 256)
-  SG_DEV_PEER_PUSH_BLOCKS = 5, // quarter-blocks per SM of the all-gather store kernel (0 = 2, i.e. one block per two SMs)
+  SG_DEV_PEER_PUSH_BLOCKS = 5, // quarter-blocks per SM of the all-gather store kernel (0 = 1, i.e. one block per four SMs)
   SG_DEV_GEMM_TRACE = 8,        // 1: accumulate wait cycles of pair 0's leader CTA (sg_gemm_trace_read)
   SG_DEV_COUNT = 12
 };

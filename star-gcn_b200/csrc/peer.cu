@@ -137,10 +137,12 @@ int sg_peer_push_rows(float *const *dst_host, const float *src, long long n_floa
   const long long n4 = n_floats / 4;
   long long blocks = ceil_div<long long>(n4, 256 * 4);
   const int dv = dev_option(SG_DEV_PEER_PUSH_BLOCKS);
-  // The stores are posted and the transfer is NVLink-bound, so a SMALL grid is enough — and it leaves the SMs to the
-  // other layer direction's gather, which runs at the same time: 8 GPUs, 17.9 MB block, step 1.794 ms with two blocks
-  // per SM, 1.790 with one, 1.751 with one block per two SMs (profiles/r02_summary.md I).
-  const long long cap = (dv > 0 ? dv : 2) * (long long)num_sms() / 4;
+  // The stores are posted and the transfer is NVLink-bound (0.20 ms for a 17.9 MB block to 8 tables whatever the
+  // grid), so a SMALL grid is enough — and it leaves the SMs to the other layer direction's gather, which runs at the
+  // same time.  8 GPUs, weak scaling, step time by grid: 296 CTAs 1.794 ms, 148: 1.790, 74: 1.750, 37: 1.690
+  // (profiles/r02_summary.md I).  One block per four SMs.
+  const long long cap = world == 1 ? 4LL * num_sms()          // a local copy (the sparse layout's own rows): HBM-bound
+                                   : (dv > 0 ? dv : 1) * (long long)num_sms() / 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   peer_push_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const float4 *>(src), n4, world);
