@@ -239,6 +239,34 @@ MAX_PEERS = 8          # SG_MAX_PEERS (include/stargcn_b200.h)
 PEER_COPY_ENGINE_BYTES = None
 
 
+def peer_sparse_layout(counts, rank):
+    """Row arithmetic of the sparse-halo peer exchange for one rank (pure; tests/test_dist_cpu.py).
+
+    counts[p] = dict(n_local, recv=[rows p fetches from q], send=[rows p sends to q]) of EVERY rank p, with
+    recv[p][q] == send[q][p].  A rank's table is [own rows ; rows fetched from rank 0, 1, ... (by id)] and its send
+    slots are ordered by requesting rank.  Returns, in ROWS:
+      send_lo    (W+1) slot ranges of the send list by requesting rank p
+      x_dst[p]   first row of p's table that this rank's block lands in (forward pack-and-push)
+      halo_lo    (W+2) row ranges of this rank's table by gradient target: [own rows | fetched from 0 | from 1 | ...]
+      g_dst[q]   first row of q's gradient staging that the slots fetched from q go back to (= where q's send list
+                 holds the block it sent to this rank)
+      n_ext, n_send, x_rows (largest table over ranks), g_rows (largest send list over ranks)"""
+    W = len(counts)
+    me = counts[rank]
+    send_lo = [0]
+    for p_ in range(W):
+        send_lo.append(send_lo[-1] + int(me["send"][p_]))
+    halo_lo = [0, int(me["n_local"])]
+    for q in range(W):
+        halo_lo.append(halo_lo[-1] + int(me["recv"][q]))
+    return dict(send_lo=send_lo, halo_lo=halo_lo,
+                x_dst=[int(counts[p_]["n_local"]) + sum(int(c) for c in counts[p_]["recv"][:rank]) for p_ in range(W)],
+                g_dst=[sum(int(c) for c in counts[q]["send"][:rank]) for q in range(W)],
+                n_ext=halo_lo[-1], n_send=send_lo[-1],
+                x_rows=max(int(c["n_local"]) + sum(int(v) for v in c["recv"]) for c in counts),
+                g_rows=max(sum(int(v) for v in c["send"]) for c in counts))
+
+
 class PeerTransport:
     """Exchange buffers of ONE layer direction in symmetric memory: every rank maps every rank's buffer, so the
     collectives of the partitioned step are this library's own kernels over NVLink peer memory (csrc/peer.cu).
@@ -288,10 +316,10 @@ class PeerTransport:
                     if allc[p_]["recv"][q] != allc[q]["send"][p_]:
                         raise RuntimeError("halo plans of the ranks do not match (recv / send counts differ)")
             self._counts = allc
-            x_rows = max(c["n_local"] + sum(c["recv"]) for c in allc)      # symmetric allocation: the largest rank's size
-            g_floats = al(max(sum(c["send"]) for c in allc) * D)
-            self.n_ext = self.n_local + sum(mine["recv"])
-            self.n_send = sum(mine["send"])
+            self._lay = lay = peer_sparse_layout(allc, rank)
+            x_rows = lay["x_rows"]                      # symmetric allocation: the largest rank's size
+            g_floats = al(lay["g_rows"] * D)
+            self.n_ext, self.n_send = lay["n_ext"], lay["n_send"]
         self.grad_capacity = al(grad_floats)
         off, pos = {}, self.FLAG_WORDS
         for name, n in (("x_ext", al(x_rows * D)), ("g_stage", g_floats), ("w_stage", W * self.grad_capacity)):
@@ -325,24 +353,16 @@ class PeerTransport:
             self._x_peer = [self.handle.get_buffer(q, (self.n_local, D), torch.float32, off["x_ext"] + lo[rank] * D)
                             for q in range(W)]
         else:
-            allc = self._counts
             self.x_ext = self.buf[off["x_ext"]:off["x_ext"] + self.n_ext * D].view(self.n_ext, D)
             self._g_stage = self.buf[off["g_stage"]:off["g_stage"] + max(self.n_send, 1) * D].view(max(self.n_send, 1), D)[:self.n_send]
-            # forward: send slot s of the block for peer p lands in p's table behind p's own rows and the rows p
-            # fetches from lower ranks
-            send_lo = [0]
-            for p_ in range(W):
-                send_lo.append(send_lo[-1] + allc[rank]["send"][p_])
-            self._send_lo = (ctypes.c_int32 * (W + 1))(*send_lo)
-            self._x_dst = table([base[p_] + 4 * (off["x_ext"] + (allc[p_]["n_local"] + sum(allc[p_]["recv"][:rank])) * D)
-                                 for p_ in range(W)])
-            # backward: rows [0, n_local) stay here (target 0, set per call); the halo slots fetched from owner q go to
-            # q's g_stage at the position of the block q sends to this rank
-            halo_lo = [0, self.n_local]
-            for q in range(W):
-                halo_lo.append(halo_lo[-1] + allc[rank]["recv"][q])
-            self._halo_lo = (ctypes.c_int32 * (W + 2))(*halo_lo)
-            self._g_dst_peers = [base[q] + 4 * (off["g_stage"] + sum(allc[q]["send"][:rank]) * D) for q in range(W)]
+            # forward: the block of send slots for peer p lands in p's table behind p's own rows and the rows p fetches
+            # from lower ranks; backward: rows [0, n_local) stay here (target 0, set per call), the halo slots fetched
+            # from owner q go to q's g_stage at the position of the block q sends to this rank (peer_sparse_layout)
+            lay = self._lay
+            self._send_lo = (ctypes.c_int32 * (W + 1))(*lay["send_lo"])
+            self._x_dst = table([base[p_] + 4 * (off["x_ext"] + lay["x_dst"][p_] * D) for p_ in range(W)])
+            self._halo_lo = (ctypes.c_int32 * (W + 2))(*lay["halo_lo"])
+            self._g_dst_peers = [base[q] + 4 * (off["g_stage"] + lay["g_dst"][q] * D) for q in range(W)]
             d = plan._dev if plan._dev is not None else plan.to(self.device)._dev
             self._send_cat = d["send_cat"]
             self._send_ptr = torch.arange(self.n_send + 1, dtype=torch.int32, device=self.device)
@@ -619,5 +639,5 @@ def partitioned_layer_inputs(base, rank, world):
     return out
 
 
-__all__ = ["HaloPlan", "PeerTransport", "halo_exchange", "partitioned_aggregate", "allreduce_grads", "contiguous_ranges", "balanced_ranges",
+__all__ = ["HaloPlan", "PeerTransport", "peer_sparse_layout", "halo_exchange", "partitioned_aggregate", "allreduce_grads", "contiguous_ranges", "balanced_ranges",
            "partitioned_layer_inputs", "edge_owner"]

@@ -141,3 +141,64 @@ def test_strong_partition_covers_the_graph_once(world):
         assert sum(edges) == base["nnz"] and los == sorted(los)
         max_deg = int(np.diff(base[key]["indptr"]).max())
         assert max(edges) - min(edges) <= 2 * max_deg + 1      # balanced up to one row's worth of edges per cut
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_sparse_layout_row_arithmetic(world):
+    """dist.peer_sparse_layout (the pointer arithmetic behind the sparse-halo peer transport) for every rank of a
+    random `world`: the forward blocks tile every receiver's table exactly as HaloPlan lays its halo out
+    ([own rows ; rows from rank 0, 1, ... by id]) and the backward blocks tile every owner's staging in send-list
+    order — simulated with numpy in place of the peer stores."""
+    from stargcn_b200 import dist as sgd
+    rs = np.random.RandomState(world)
+    D = 4
+    n_local = [int(v) for v in rs.randint(3, 30, size=world)]
+    # requested rows: want[p][q] = sorted distinct local row ids of q that p fetches (p != q), some empty
+    want = [[np.sort(rs.choice(n_local[q], size=rs.randint(0, n_local[q] + 1), replace=False)) if (p != q and rs.rand() > 0.2)
+             else np.zeros(0, np.int64) for q in range(world)] for p in range(world)]
+    counts = [dict(n_local=n_local[p], recv=[len(want[p][q]) for q in range(world)], send=[len(want[q][p]) for q in range(world)])
+              for p in range(world)]
+    lays = [sgd.peer_sparse_layout(counts, r) for r in range(world)]
+    x = [rs.normal(size=(n_local[p], D)) for p in range(world)]
+    # ---- forward: every rank packs the rows each peer asked for and stores them into that peer's table ----
+    tables = [np.full((lays[0]["x_rows"], D), np.nan) for _ in range(world)]
+    written = [np.zeros(lays[0]["x_rows"], np.int32) for _ in range(world)]
+    for r in range(world):
+        tables[r][:n_local[r]] = x[r]
+        written[r][:n_local[r]] += 1
+        send_cat = np.concatenate([want[p][r] for p in range(world)]).astype(np.int64)      # r's send list, by requesting rank
+        assert lays[r]["n_send"] == send_cat.size and lays[r]["send_lo"][-1] == send_cat.size
+        for p in range(world):
+            a, b = lays[r]["send_lo"][p], lays[r]["send_lo"][p + 1]
+            dst = lays[r]["x_dst"][p]
+            tables[p][dst:dst + (b - a)] = x[r][send_cat[a:b]]
+            written[p][dst:dst + (b - a)] += 1
+    for p in range(world):
+        n_ext = lays[p]["n_ext"]
+        assert n_ext == n_local[p] + sum(counts[p]["recv"]) and n_ext <= lays[p]["x_rows"]
+        assert np.all(written[p][:n_ext] == 1) and np.all(written[p][n_ext:] == 0)           # tiled exactly once
+        expect = np.concatenate([x[p]] + [x[q][want[p][q]] for q in range(world)])
+        assert np.array_equal(tables[p][:n_ext], expect)
+    # ---- backward: every rank stores the gradient of each fetched slot into its owner's staging ----
+    g_ext = [rs.normal(size=(lays[p]["n_ext"], D)) for p in range(world)]
+    stage = [np.full((lays[0]["g_rows"], D), np.nan) for _ in range(world)]
+    hits = [np.zeros(lays[0]["g_rows"], np.int32) for _ in range(world)]
+    for r in range(world):
+        hl = lays[r]["halo_lo"]
+        assert hl[0] == 0 and hl[1] == n_local[r] and hl[-1] == lays[r]["n_ext"] and len(hl) == world + 2
+        for q in range(world):
+            a, b = hl[1 + q], hl[2 + q]
+            dst = lays[r]["g_dst"][q]
+            stage[q][dst:dst + (b - a)] = g_ext[r][a:b]
+            hits[q][dst:dst + (b - a)] += 1
+    for q in range(world):
+        n_send = lays[q]["n_send"]
+        assert np.all(hits[q][:n_send] == 1) and np.all(hits[q][n_send:] == 0)
+        send_cat = np.concatenate([want[p][q] for p in range(world)]).astype(np.int64)
+        got = g_ext[q][:n_local[q]].copy()
+        np.add.at(got, send_cat, stage[q][:n_send])                                            # the owner's sorted-transpose sum
+        expect = g_ext[q][:n_local[q]].copy()
+        for p in range(world):
+            off = n_local[p] + sum(counts[p]["recv"][:q])
+            np.add.at(expect, want[p][q], g_ext[p][off:off + len(want[p][q])])
+        assert np.allclose(got, expect, rtol=0, atol=1e-12)
