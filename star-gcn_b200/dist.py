@@ -572,6 +572,7 @@ def partitioned_aggregate(agg, x_local, plan, *plan_lists):
     ``x_local`` and its CSR (a MultiLinkCSR or the three per-level lists, column ids = ``plan.local_cols``).
     Mode 'peer' runs the exchange inside the fused op (NVLink peer memory); the NCCL modes exchange first."""
     if plan is None:
+        agg.halo_plan = None
         return agg(x_local, *plan_lists)
     if plan.mode == "peer":
         agg.halo_plan = plan
