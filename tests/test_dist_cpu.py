@@ -202,3 +202,31 @@ def test_peer_sparse_layout_row_arithmetic(world):
             off = n_local[p] + sum(counts[p]["recv"][:q])
             np.add.at(expect, want[p][q], g_ext[p][off:off + len(want[p][q])])
         assert np.allclose(got, expect, rtol=0, atol=1e-12)
+
+
+def test_halo_plan_modes_without_a_process_group():
+    """Mode / layout choice of HaloPlan where no collective is needed (exchange_fn given or forced modes)."""
+    from stargcn_b200 import dist as sgd
+    ranges = np.array([0, 10, 20, 30])
+    cols_dense = np.arange(30)                       # rank 1 references every row of every rank
+    cols_sparse = np.array([10, 11, 12, 0, 29])      # ... or 2 of the 20 remote rows
+    echo = lambda req: [np.zeros(0, np.int32) for _ in req]
+    for mode, cols, want in (("peer_dense", cols_sparse, ("peer", True)), ("peer_sparse", cols_dense, ("peer", False)),
+                             ("alltoall", cols_dense, ("alltoall", False)), ("allgather", cols_sparse, ("allgather", True)),
+                             ("auto", cols_dense, ("allgather", True)), ("auto", cols_sparse, ("alltoall", False)),
+                             ("nccl", cols_dense, ("allgather", True)), ("peer", cols_dense, ("peer", True)),
+                             ("peer", cols_sparse, ("peer", False))):
+        plan = sgd.HaloPlan(cols, ranges, 1, 3, exchange_fn=echo, mode=mode)
+        assert (plan.mode, plan.dense) == want, (mode, plan.mode, plan.dense)
+        if plan.dense:
+            assert plan.n_ext == 30 and np.array_equal(plan.local_cols, cols)
+        else:
+            assert plan.n_local == 10 and plan.n_ext == 10 + np.unique(cols[(cols < 10) | (cols >= 20)]).size
+    with pytest.raises(ValueError):
+        sgd.HaloPlan(cols_dense, ranges, 1, 3, exchange_fn=echo, mode="bogus")
+    with pytest.raises(ValueError):                   # unequal blocks cannot use the NCCL all-gather
+        sgd.HaloPlan(np.arange(25), np.array([0, 10, 25]), 0, 2, exchange_fn=echo, mode="allgather")
+    with pytest.raises(ValueError):                   # one NVSwitch box: at most 8 ranks over peer memory
+        sgd.HaloPlan(np.arange(9), np.arange(10), 0, 9, exchange_fn=echo, mode="peer_dense")
+    with pytest.raises(ValueError):
+        sgd.HaloPlan(np.array([31]), ranges, 1, 3, exchange_fn=echo, mode="alltoall")
