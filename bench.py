@@ -792,7 +792,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     else:
         result["collective"] = dict(mode=modes, halo_rows_rank0=halo_by_side)
         if exchange:
-            n_prof = max(min(args.steps, 20), 1)
+            n_prof = max(sum(1 for tag, _a, _b, c in prof if tag == "agg_fwd" and c is sides["user"]["csr"]), 1)   # profiled steps
             result["collective"]["exchange_ms_per_step_rank0"] = {k: round(v["ms"] / n_prof, 5) for k, v in sorted(exchange.items())}
             result["collective"]["exchange_note"] = ("CUDA events around the exchange launches in the eager single-stream pass after the "
                                                      "timed region: peer_push = all-gather stores / copies, peer_barrier = flag barrier "
